@@ -1,0 +1,94 @@
+"""ctypes loader of libsvr_b200.so (the C ABI declared in include/svr_abi.h).
+
+Fails loudly if the library is missing or cannot be loaded: there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libsvr_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "svr_abi.h")
+
+_lib = None
+
+vp, ip, fp, dp = C.c_void_p, C.c_int, C.c_float, C.c_double
+F = C.POINTER(C.c_float)
+I = C.POINTER(C.c_int)
+D = C.POINTER(C.c_double)
+U8 = C.POINTER(C.c_ubyte)
+
+_SIGNATURES = {
+    "svr_create": (ip, [C.POINTER(vp), ip]),
+    "svr_destroy": (ip, [vp]),
+    "svr_last_error": (C.c_char_p, [vp]),
+    "svr_abi_version": (ip, []),
+    "svr_set_stream": (ip, [vp, vp]),
+    "svr_synchronize": (ip, [vp]),
+    "svr_launch_count": (C.c_int64, [vp]),
+    "svr_init_reconstruction_volume": (ip, [vp, ip, ip, ip, fp, fp, fp, vp]),
+    "svr_set_mask": (ip, [vp, ip, ip, ip, vp]),
+    "svr_init_storage_volumes": (ip, [vp, ip, ip, ip]),
+    "svr_fill_slices": (ip, [vp, vp, vp, vp]),
+    "svr_set_slice_dims": (ip, [vp, vp, fp]),
+    "svr_set_slice_matrices": (ip, [vp, vp, vp, vp, vp, vp, vp]),
+    "svr_generate_psf_volume": (ip, [vp, vp, vp, fp]),
+    "svr_update_scale_vector": (ip, [vp, vp, vp]),
+    "svr_update_slice_weights": (ip, [vp, vp]),
+    "svr_update_reconstructed": (ip, [vp, vp]),
+    "svr_initialize_em_values": (ip, [vp]),
+    "svr_gaussian_reconstruction": (ip, [vp, vp]),
+    "svr_simulate_slices": (ip, [vp, vp]),
+    "svr_initialize_robust_statistics": (ip, [vp, F]),
+    "svr_estep": (ip, [vp, fp, fp, fp, vp]),
+    "svr_mstep": (ip, [vp, ip, fp, F, F, F]),
+    "svr_calculate_scale_vector": (ip, [vp, vp]),
+    "svr_superresolution": (ip, [vp, ip, vp, ip, fp, fp, fp, fp, fp]),
+    "svr_mask_volume": (ip, [vp]),
+    "svr_scale_volume": (ip, [vp, F]),
+    "svr_restore_slice_intensities": (ip, [vp, vp, ip, vp]),
+    "svr_sync_cpu": (ip, [vp, vp]),
+    "svr_get_vol_weights": (ip, [vp, vp]),
+    "svr_debug_get": (ip, [vp, ip, vp]),
+    "svr_gaussian_reconstruction_local": (ip, [vp]),
+    "svr_gaussian_reconstruction_finish": (ip, [vp, vp]),
+    "svr_superresolution_local": (ip, [vp, vp]),
+    "svr_superresolution_finish": (ip, [vp, ip, fp, fp, fp, fp, fp]),
+    "svr_mstep_local": (ip, [vp, D]),
+    "svr_mstep_finish": (ip, [D, ip, fp, F, F, F]),
+    "svr_initialize_robust_statistics_local": (ip, [vp, D]),
+    "svr_scale_volume_local": (ip, [vp, D]),
+    "svr_scale_volume_apply": (ip, [vp, fp]),
+    "svr_device_buffer": (ip, [vp, ip, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "svr_host_slice_em": (ip, [ip, vp, vp, vp, vp, ip, vp, ip, dp, vp]),
+    "svr_host_small_slices": (ip, [ip, vp, vp, I]),
+    "svr_host_partition": (ip, [ip, vp, ip, ip, I, I]),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Every function include/svr_abi.h declares (used by the CPU test that checks the exports)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(svr_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """dlopen the library and attach the prototypes.  Raises if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m fetalreconstruction_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,186 @@
+/*
+ * svr_abi.h -- C ABI of libsvr_b200.so: the B200-native SVR (slice-to-volume reconstruction) device
+ * library.  It is a drop-in for the public method set of `class Reconstruction` of
+ * bkainz/fetalReconstruction (source/reconstructionGPU2/include/reconstruction_cuda2.cuh:92-341),
+ * i.e. the boundary `irtkReconstruction::*GPU()` calls into (irtkReconstructionGPU.cc).
+ *
+ * Conventions
+ *   - plain C types only: host pointers, sizes, scalars; matrices are float[16] row-major
+ *     (the reference's Matrix4 = float4 data[4], recon_volumeHelper.cuh:41-46).
+ *   - every call returns 0 on success, non-zero on failure; svr_last_error() gives the text.
+ *     (The reference prints and exit()s, reconstruction_cuda2.cuh:78-86; a CLI built on this
+ *     library does the exit itself.)
+ *   - one context = one GPU = one rank.  Calls are synchronous with respect to the host like the
+ *     reference's (each returns after its stream work is complete) unless stated otherwise.
+ *   - volumes are x-fastest: idx = x + y*sx + z*sx*sy; the slice cube is float[S][Ny][Nx] with
+ *     -1 marking padding (irtkReconstructionGPU.cc:269-314).
+ *   - there is no CPU fallback: without a CUDA device svr_create fails.
+ *
+ * "ref:" cites the reference interface each entry replaces (paths relative to
+ * source/reconstructionGPU2/; cuda2.cu = reconstruction_cuda2.cu, .cuh = include/reconstruction_cuda2.cuh).
+ */
+#ifndef SVR_ABI_H
+#define SVR_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVR_ABI_VERSION 1
+
+typedef struct svr_context svr_context;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* ref: Reconstruction::Reconstruction(std::vector<int> dev, bool) .cuh:94, cuda2.cu:616-706.
+ * One device per context (multi-GPU = one context per rank, section "multi-rank" below). */
+int svr_create(svr_context **out, int device);
+/* ref: Reconstruction::~Reconstruction cuda2.cu:1232-1310 */
+int svr_destroy(svr_context *ctx);
+const char *svr_last_error(const svr_context *ctx);   /* ctx may be NULL: error of a failed svr_create */
+int svr_abi_version(void);
+/* Run all work of this context on a caller-owned cudaStream_t (NULL = the context's own stream).
+ * ref: cudaStream_t streams[] .cuh:141 */
+int svr_set_stream(svr_context *ctx, void *cuda_stream);
+/* Block until all queued work of the context is complete.  ref: cudaDeviceSynchronize calls. */
+int svr_synchronize(svr_context *ctx);
+/* Number of kernels this context has launched since creation (for bench.py's gpu_launches). */
+int64_t svr_launch_count(const svr_context *ctx);
+
+/* ---- uploads ---------------------------------------------------------------------------- */
+/* ref: InitReconstructionVolume(uint3 s, float3 dim, float* data, float sigma_bias) .cuh:230,
+ * cuda2.cu:1160-1230.  data may be NULL (zeros).  dim = voxel size in mm. */
+int svr_init_reconstruction_volume(svr_context *ctx, int sx, int sy, int sz, float dx, float dy, float dz,
+                                   const float *data);
+/* ref: setMask(uint3, float3, float* data, float sigma_bias) .cuh:240, cuda2.cu:1095-1158.
+ * (The smoothed copy maskC_ only feeds the unreachable bias correction and is not built.) */
+int svr_set_mask(svr_context *ctx, int sx, int sy, int sz, const float *mask);
+/* ref: initStorageVolumes(uint3 size, float3 dim) .cuh:214, cuda2.cu:1408-1573.  Allocates the
+ * per-pixel buffers for S slices of Nx x Ny pixels.  All S slices are kept (deviation D2). */
+int svr_init_storage_volumes(svr_context *ctx, int Nx, int Ny, int S);
+/* ref: FillSlices(float* sdata, vector<int> sizesX, vector<int> sizesY) .cuh:216, cuda2.cu:1574-1656.
+ * sizesX/sizesY may be NULL (they are informational in the reference too). */
+int svr_fill_slices(svr_context *ctx, const float *cube, const int *sizesX, const int *sizesY);
+/* ref: setSliceDims(vector<float3> slice_dims, float quality_factor) .cuh:220, cuda2.cu:772-833. */
+int svr_set_slice_dims(svr_context *ctx, const float *dims_xyz /* [S][3] */, float quality_factor);
+/* ref: SetSliceMatrices(T, Tinv, I2Winit, W2Iinit, I2W, W2I, reconI2W, reconW2I) .cuh:222-224,
+ * cuda2.cu:835-907.  All per-slice arrays are [S][16]. */
+int svr_set_slice_matrices(svr_context *ctx, const float *transforms, const float *inv_transforms,
+                           const float *slices_i2w, const float *slices_w2i, const float recon_i2w[16],
+                           const float recon_w2i[16]);
+/* ref: generatePSFVolume(float* psf, uint3, float3, float3, Matrix4 PSFI2W, Matrix4 PSFW2I, float q)
+ * .cuh:218, cuda2.cu:718-750 (uploads constants only; the sampled PSF volume is never read). */
+int svr_generate_psf_volume(svr_context *ctx, const int psf_size[3], const float psf_i2w[16], float quality_factor);
+/* ref: UpdateScaleVector(vector<float> scales, vector<float> slice_weights) .cuh:236, cuda2.cu:1342-1393 */
+int svr_update_scale_vector(svr_context *ctx, const float *scales, const float *slice_weights);
+/* ref: UpdateSliceWeights(vector<float>) .cuh:228, cuda2.cu:1312-1340 */
+int svr_update_slice_weights(svr_context *ctx, const float *slice_weights);
+/* ref: UpdateReconstructed(uint3, float* data) .cuh:233, cuda2.cu:1658-1668 */
+int svr_update_reconstructed(svr_context *ctx, const float *data);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+/* ref: InitializeEMValues() .cuh:211, cuda2.cu:3241-3310 (K12) */
+int svr_initialize_em_values(svr_context *ctx);
+/* ref: GaussianReconstruction(vector<int>& voxel_num) .cuh:274, cuda2.cu:2329-2493 (K1, K6, K14).
+ * voxel_num[S] (may be NULL): per-SLICE count of pixels that touched the masked volume (deviation D4). */
+int svr_gaussian_reconstruction(svr_context *ctx, int *voxel_num);
+/* ref: SimulateSlices(vector<bool>& slice_inside) .cuh:257, cuda2.cu:2654-2763 (K2, K13). slice_inside[S] may be NULL. */
+int svr_simulate_slices(svr_context *ctx, unsigned char *slice_inside);
+/* ref: InitializeRobustStatistics(float& sigma) .cuh:260, cuda2.cu:2243-2308 (K11) */
+int svr_initialize_robust_statistics(svr_context *ctx, float *sigma);
+/* ref: EStep(float m, float sigma, float mix, vector<float>& slice_potential) .cuh:253, cuda2.cu:2766-2925 (K7, K8) */
+int svr_estep(svr_context *ctx, float m, float sigma, float mix, float *slice_potential);
+/* ref: MStep(int iter, float step, float& sigma, float& mix, float& m) .cuh:255, cuda2.cu:2927-3112 (K9) */
+int svr_mstep(svr_context *ctx, int iter, float step, float *sigma, float *mix, float *m);
+/* ref: CalculateScaleVector(vector<float>& scale_vec) .cuh:238, cuda2.cu:3114-3239 (K10).
+ * Reproduces the reference's upload order: the device keeps the PREVIOUS scale vector for the
+ * kernels (cuda2.cu:3238 copies h_scales before cuda2.cu:3195 updates it); the M-step uses the new one. */
+int svr_calculate_scale_vector(svr_context *ctx, float *scale_vec);
+/* ref: Superresolution(int iter, vector<float> slice_weight, bool adaptive, float alpha, float min_intensity,
+ * float max_intensity, float delta, float lambda, bool global_bias, float sigma_bias, float low_cutoff)
+ * .cuh:263-265, cuda2.cu:2119-2241 (K3, K4, K5).  slice_weight may be NULL (keep the uploaded vector). */
+int svr_superresolution(svr_context *ctx, int iter, const float *slice_weight, int adaptive, float alpha,
+                        float min_intensity, float max_intensity, float delta, float lambda);
+/* ref: maskVolume() .cuh:270, cuda2.cu:3313-3347 (K15) */
+int svr_mask_volume(svr_context *ctx);
+/* ref: ScaleVolume() .cuh:271, cuda2.cu:3386-3470 (K16).  scale_out may be NULL. */
+int svr_scale_volume(svr_context *ctx, float *scale_out);
+/* ref: RestoreSliceIntensities(vector<float> stack_factors, vector<int> stack_index) .cuh:272, cuda2.cu:3349-3383 (K17).
+ * As in the reference this rescales the restore-copy of the slices (v_slices), not the working set. */
+int svr_restore_slice_intensities(svr_context *ctx, const float *stack_factors, int n_stacks, const int *stack_index);
+
+/* ---- downloads -------------------------------------------------------------------------- */
+/* ref: syncCPU(float* reconstructed) .cuh:213, cuda2.cu:2031-2037 */
+int svr_sync_cpu(svr_context *ctx, float *reconstructed);
+/* ref: getVolWeights(float*) .cuh:206 */
+int svr_get_vol_weights(svr_context *ctx, float *weights);
+
+/* Debug taps.  ref: debugWeights/Simslices/Simweights/Siminside/ConfidenceMap/Addon/v_PSF_sums .cuh:192-207
+ * (+ the slice cube, the restore copy and the K1 voxel counts). */
+enum svr_debug_kind {
+    SVR_DBG_WEIGHTS = 0,        /* float[S*Ny*Nx] */
+    SVR_DBG_SIMSLICES = 1,      /* float[S*Ny*Nx] */
+    SVR_DBG_SIMWEIGHTS = 2,     /* float[S*Ny*Nx] */
+    SVR_DBG_SIMINSIDE = 3,      /* char [S*Ny*Nx] */
+    SVR_DBG_CONFIDENCE_MAP = 4, /* float[V] */
+    SVR_DBG_ADDON = 5,          /* float[V] */
+    SVR_DBG_PSF_SUMS = 6,       /* float[S*Ny*Nx] */
+    SVR_DBG_SLICES = 7,         /* float[S*Ny*Nx] */
+    SVR_DBG_VOXEL_COUNT = 8,    /* int  [S*Ny*Nx] */
+    SVR_DBG_SLICES_RESTORED = 9,/* float[S*Ny*Nx] */
+    SVR_DBG_SCALES_DEVICE = 10, /* float[S]: the scale vector the kernels see */
+    SVR_DBG_MASK = 11           /* float[V] */
+};
+int svr_debug_get(svr_context *ctx, int kind, void *out);
+
+/* ---- multi-rank (one process per GPU; stacks sharded; volume accumulators all-reduced) ----
+ * The reference reduces to device 0 and re-broadcasts (cuda2.cu:2225-2239, 2445-2460, 2175-2180).
+ * Here every rank holds its own slices and a full replica of the volume; the split-phase calls
+ * below expose the exchange points so the caller can all-reduce the accumulator (NCCL over
+ * NVLink: ncclAllReduce or torch.distributed on svr_device_buffer()) between the two halves.
+ * svr_gaussian_reconstruction == _local + _finish; svr_superresolution == _local + _finish. */
+int svr_gaussian_reconstruction_local(svr_context *ctx);
+int svr_gaussian_reconstruction_finish(svr_context *ctx, int *voxel_num);
+int svr_superresolution_local(svr_context *ctx, const float *slice_weight);
+int svr_superresolution_finish(svr_context *ctx, int adaptive, float alpha, float min_intensity, float max_intensity,
+                               float delta, float lambda);
+/* Partial statistics (this rank's slices); sum / min / max them over ranks, then *_finish.
+ * sums5 = {sum e^2 w, sum w, n, min e, max e}   (ref: MStepOnX cuda2.cu:3074-3112) */
+int svr_mstep_local(svr_context *ctx, double sums5[5]);
+/* Pure host arithmetic of Reconstruction::MStep, cuda2.cu:3056-3071. */
+int svr_mstep_finish(const double sums5[5], int iter, float step, float *sigma, float *mix, float *m);
+/* sums2 = {sum (s-sim)^2, n}  (ref: cuda2.cu:2296-2305) */
+int svr_initialize_robust_statistics_local(svr_context *ctx, double sums2[2]);
+/* sums2 = {scalenum, scaleden}  (ref: cuda2.cu:3446-3454); then svr_scale_volume_apply on every rank. */
+int svr_scale_volume_local(svr_context *ctx, double sums2[2]);
+int svr_scale_volume_apply(svr_context *ctx, float scale);
+
+enum svr_buffer_kind {
+    SVR_BUF_ACCUMULATOR = 0, /* float2[V], interleaved {numerator, denominator}: {sum psf*s, sum psf} after
+                                svr_gaussian_reconstruction_local, {addon, cmap} after svr_superresolution_local */
+    SVR_BUF_RECON = 1        /* float[V] */
+};
+/* Device address + byte size of a context-owned buffer (for collectives issued by the caller on the
+ * context's stream).  Valid until svr_destroy / re-initialisation of the volume. */
+int svr_device_buffer(svr_context *ctx, int kind, void **dev_ptr, size_t *nbytes);
+
+/* ---- pure host helpers (no device work; usable without a GPU) ---------------------------- */
+/* Slice-level EM of irtkReconstruction::EStepGPU, irtkReconstructionGPU.cc:3184-3440.
+ * slice_potential[S] in/out (exclusions set to -1), scale[S], slice_weight[S] in/out,
+ * state5 = {sigma_s, mix_s, mean_s, mean_s2, sigma_s2} in/out. */
+int svr_host_slice_em(int S, float *slice_potential, const float *scale, float *slice_weight, const int *force_excluded,
+                      int n_force_excluded, const int *small_slices, int n_small_slices, double step, float state5[5]);
+/* "Small slices" rule of GaussianReconstructionGPU, irtkReconstructionGPU.cc:2714-2726, applied to
+ * per-slice counts (deviation D4).  out_small[S] receives indices; returns their number via n_out. */
+int svr_host_small_slices(int S, const int *voxel_num, int *out_small, int *n_out);
+/* Contiguous, balanced assignment of whole stacks (or of slices when n_stacks < nranks) to ranks.
+ * slices_per_stack[n_stacks]; out_begin/out_end = this rank's [begin,end) in global slice order.
+ * ref (what it replaces): floor(N/D)-sized ranges that drop the remainder, cuda2.cu:1413-1457. */
+int svr_host_partition(int n_stacks, const int *slices_per_stack, int nranks, int rank, int *out_begin, int *out_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVR_ABI_H */
