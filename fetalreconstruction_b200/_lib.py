@@ -62,6 +62,9 @@ _SIGNATURES = {
     "svr_scale_volume_local": (ip, [vp, D]),
     "svr_scale_volume_apply": (ip, [vp, fp]),
     "svr_device_buffer": (ip, [vp, ip, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "svr_profile_enable": (ip, [vp, ip]),
+    "svr_profile_read": (ip, [vp, ip, D, C.POINTER(C.c_int64)]),
+    "svr_profile_reset": (ip, [vp]),
     "svr_host_slice_em": (ip, [ip, vp, vp, vp, vp, ip, vp, ip, dp, vp]),
     "svr_host_small_slices": (ip, [ip, vp, vp, I]),
     "svr_host_partition": (ip, [ip, vp, ip, ip, I, I]),

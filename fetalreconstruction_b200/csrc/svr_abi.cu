@@ -24,6 +24,36 @@ static int fail_msg(svr_context* ctx, const char* msg)
 }
 #define REQUIRE(ctx, cond, msg) do { if (!(cond)) return fail_msg((ctx), (msg)); } while (0)
 
+static cudaEvent_t prof_event(svr_context* c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+ProfScope::ProfScope(svr_context* ctx, int kind) : c(ctx), idx(-1)
+{
+    if (!c->prof_on) return;
+    svr_context::ProfPair p{ prof_event(c), prof_event(c), kind };
+    cudaEventRecord(p.a, c->stream);
+    c->prof_pending.push_back(p);
+    idx = (int)c->prof_pending.size() - 1;
+}
+ProfScope::~ProfScope()
+{
+    if (idx >= 0) cudaEventRecord(c->prof_pending[idx].b, c->stream);
+}
+static void prof_fold(svr_context* c)
+{
+    cudaStreamSynchronize(c->stream);
+    for (auto& p : c->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { c->prof_ms[p.kind] += ms; c->prof_n[p.kind] += 1; }
+        c->prof_pool.push_back(p.a); c->prof_pool.push_back(p.b);
+    }
+    c->prof_pending.clear();
+}
+
 template <class T>
 static int dev_alloc(svr_context* c, T** p, size_t n)
 {
@@ -77,6 +107,8 @@ int svr_destroy(svr_context* c)
     dev_free(&c->valid_idx); dev_free(&c->slice_count); dev_free(&c->slice_inside); dev_free(&c->scales);
     dev_free(&c->scales_mstep); dev_free(&c->slice_weights); dev_free(&c->slice_tmp); dev_free(&c->geom);
     dev_free(&c->mats); dev_free(&c->dims); dev_free(&c->partials);
+    prof_fold(c);
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->cub_tmp) cudaFree(c->cub_tmp);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -100,6 +132,29 @@ int svr_synchronize(svr_context* c)
 }
 
 int64_t svr_launch_count(const svr_context* c) { return c ? c->launches : 0; }
+
+int svr_profile_enable(svr_context* c, int on)
+{
+    REQUIRE(c, c, "null context");
+    if (!on) prof_fold(c);
+    c->prof_on = on != 0;
+    return 0;
+}
+int svr_profile_read(svr_context* c, int kind, double* total_ms, int64_t* launches)
+{
+    REQUIRE(c, c && kind >= 0 && kind < SVR_K_COUNT, "svr_profile_read: bad argument");
+    prof_fold(c);
+    if (total_ms) *total_ms = c->prof_ms[kind];
+    if (launches) *launches = c->prof_n[kind];
+    return 0;
+}
+int svr_profile_reset(svr_context* c)
+{
+    REQUIRE(c, c, "null context");
+    prof_fold(c);
+    for (int i = 0; i < 8; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 static int upload(svr_context* c, void* dst, const void* src, size_t bytes)

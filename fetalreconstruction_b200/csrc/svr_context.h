@@ -60,6 +60,14 @@ struct svr_context {
     void* cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
 
+    // per-kernel device timing (svr_profile_*): event pairs recorded on the launching stream
+    struct ProfPair { cudaEvent_t a, b; int kind; };
+    bool prof_on = false;
+    std::vector<ProfPair> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[8] = {0};
+    long long prof_n[8] = {0};
+
     VolGeom vg{};
     float recon_i2w[16]{}, recon_w2i[16]{};
     float quality_factor = 1.0f;
@@ -79,6 +87,13 @@ int svr_fail(svr_context* ctx, const char* what, cudaError_t e, const char* file
         cudaError_t _e = cudaGetLastError();                                       \
         if (_e != cudaSuccess) return svr_fail((ctx), "kernel launch", _e, __FILE__, __LINE__); \
     } while (0)
+
+// RAII event bracket around a launch (no-op unless svr_profile_enable(ctx, 1))
+struct ProfScope {
+    svr_context* c; int idx;
+    ProfScope(svr_context* ctx, int kind);
+    ~ProfScope();
+};
 
 // launchers implemented in svr_psf.cu / svr_em.cu
 int svr_launch_build_geom(svr_context* c);

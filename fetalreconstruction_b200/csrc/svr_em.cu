@@ -86,6 +86,7 @@ static inline dim3 slice_grid(const svr_context* c)
 
 int svr_launch_estep(svr_context* c, float m, float sigma, float mix)
 {
+    ProfScope prof(c, 4);
     double* acc = c->partials;                            // [2*S] doubles, zeroed
     SVR_CUDA(c, cudaMemsetAsync(acc, 0, sizeof(double) * 2 * c->S, c->stream));
     estep_kernel<<<slice_grid(c), EM_THREADS, 0, c->stream>>>(c->Nx * c->Ny, c->slices, c->simslices, c->simweights,
@@ -131,6 +132,7 @@ __global__ void scale_finish_kernel(int S, const double* __restrict__ slice_acc,
 }
 int svr_launch_scale(svr_context* c)
 {
+    ProfScope prof(c, 4);
     double* acc = c->partials;
     SVR_CUDA(c, cudaMemsetAsync(acc, 0, sizeof(double) * 2 * c->S, c->stream));
     scale_kernel<<<slice_grid(c), EM_THREADS, 0, c->stream>>>(c->Nx * c->Ny, c->slices, c->weights, c->simslices,
@@ -211,6 +213,7 @@ static int read_back(svr_context* c, const double* dsrc, double* out, int n)
 
 int svr_launch_mstep(svr_context* c, double out5[5])
 {
+    ProfScope prof(c, 4);
     const int nb = c->sm_count * 4;
     double* part = c->partials;                           // [nb*5] + result [8]
     double* res = c->partials + (size_t)nb * 5;
@@ -244,6 +247,7 @@ robust_init_kernel(size_t NP, const float* __restrict__ slices, const unsigned c
 }
 int svr_launch_robust_init(svr_context* c, double out2[2])
 {
+    ProfScope prof(c, 4);
     const int nb = c->sm_count * 4;
     double* part = c->partials;
     double* res = c->partials + (size_t)nb * 5;
@@ -410,6 +414,7 @@ reg_kernel(int vx, int vy, int vz, const float* __restrict__ original, const flo
 
 int svr_launch_regularize(svr_context* c, int adaptive, float alpha, float min_i, float max_i, float delta, float lambda)
 {
+    ProfScope prof(c, 3);
     reg_prep_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->recon, c->acc2, c->recon_tmp1, adaptive, alpha, min_i, max_i);
     SVR_KERNEL_CHECK(c);
     dim3 block(64, 4, 1), grid(divup_i(c->vx, 64), divup_i(c->vy, 4), c->vz);

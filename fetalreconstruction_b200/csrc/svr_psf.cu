@@ -101,6 +101,7 @@ gaussian_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx
 int svr_launch_gaussian_scatter(svr_context* c)
 {
     if (c->n_valid == 0) return 0;
+    ProfScope prof(c, 0);
     gaussian_scatter_kernel<<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
         c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2,
         c->psf_sums, c->voxel_flag, c->slice_count);
@@ -145,6 +146,7 @@ simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx
 int svr_launch_simulate(svr_context* c)
 {
     if (c->n_valid == 0) return 0;
+    ProfScope prof(c, 1);
     simulate_kernel<<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->geom,
                                                                      c->vg, c->pack2, c->psf_sums, c->simslices,
                                                                      c->simweights, c->siminside, c->slice_inside);
@@ -188,6 +190,7 @@ superres_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx
 int svr_launch_superres_scatter(svr_context* c)
 {
     if (c->n_valid == 0) return 0;
+    ProfScope prof(c, 2);
     superres_scatter_kernel<<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
         c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
         c->geom, c->vg, c->mask_u8, c->psf_sums, c->acc2);

@@ -95,7 +95,10 @@ def _phantom_at(world: torch.Tensor, centres, radii, amps) -> torch.Tensor:
     return out
 
 
-def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: bool = True) -> Dataset:
+def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: bool = True,
+                 stacks: range | None = None) -> Dataset:
+    """`stacks` restricts generation to a contiguous range of stacks (a rank's shard); every stack is
+    seeded on its own, so the slices are identical however the stacks are sharded."""
     rng = np.random.default_rng(cfg.seed)
     vx, vy, vz = cfg.vol_size
     vol_attr = ImageAttributes(vx, vy, vz, cfg.vol_voxel, cfg.vol_voxel, cfg.vol_voxel)
@@ -120,7 +123,8 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
 
     Nx, Ny = cfg.slice_size
     thickness = cfg.thickness if cfg.thickness is not None else 2.0 * cfg.spacing
-    S = cfg.n_stacks * cfg.slices_per_stack
+    stacks = range(cfg.n_stacks) if stacks is None else stacks
+    S = len(stacks) * cfg.slices_per_stack
     slices = np.empty((S, Ny, Nx), np.float32)
     i2w = np.empty((S, 16), np.float32)
     w2i = np.empty((S, 16), np.float32)
@@ -135,7 +139,7 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
     sizes = torch.tensor([vx, vy, vz], device=dev)
 
     k = 0
-    for st in range(cfg.n_stacks):
+    for st in stacks:
         srng = np.random.default_rng(cfg.seed + st)
         if st < len(_STACK_ANGLES):
             ang = _STACK_ANGLES[st]
@@ -156,7 +160,7 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
             world = pix @ M[:3, :3].T + M[:3, 3]
             val = _phantom_at(world, centres, radii, amps) * gain
             if cfg.noise > 0:
-                g = torch.Generator(device="cpu").manual_seed(cfg.seed * 131 + k)
+                g = torch.Generator(device="cpu").manual_seed(cfg.seed * 131 + st * cfg.slices_per_stack + j)
                 val = val + cfg.noise * torch.randn(val.shape, generator=g).to(dev)
             if srng.uniform() < cfg.corrupt_fraction:
                 val = val * 0.3

@@ -79,6 +79,23 @@ class Reconstruction:
     def launch_count(self) -> int:
         return int(self._lib.svr_launch_count(self._h))
 
+    KERNEL_KINDS = ("gaussian", "simulate", "superres", "regularize", "em")
+
+    def profile_enable(self, on: bool = True):
+        self._ck(self._lib.svr_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._ck(self._lib.svr_profile_reset(self._h))
+
+    def profile_read(self) -> dict:
+        """{kind: (total device ms, launches)} measured with CUDA events on the launching stream."""
+        out = {}
+        for i, name in enumerate(self.KERNEL_KINDS):
+            ms, n = C.c_double(), C.c_int64()
+            self._ck(self._lib.svr_profile_read(self._h, i, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     @property
     def V(self):
         return self.vol_shape[0] * self.vol_shape[1] * self.vol_shape[2]

@@ -166,6 +166,22 @@ enum svr_buffer_kind {
  * context's stream).  Valid until svr_destroy / re-initialisation of the volume. */
 int svr_device_buffer(svr_context *ctx, int kind, void **dev_ptr, size_t *nbytes);
 
+/* ---- per-kernel device timing (CUDA events on the launching stream; for bench.py's roofline) ---- */
+enum svr_kernel_kind {
+    SVR_K_GAUSSIAN = 0,   /* K1  gaussian_scatter_kernel  */
+    SVR_K_SIMULATE = 1,   /* K2  simulate_kernel          */
+    SVR_K_SUPERRES = 2,   /* K3  superres_scatter_kernel  */
+    SVR_K_REGULARIZE = 3, /* K4+K5                        */
+    SVR_K_EM = 4,         /* E-step, M-step, scale, robust-init reductions */
+    SVR_K_COUNT = 5
+};
+/* When enabled every launch of the kinds above is bracketed by a cudaEvent pair (no host sync). */
+int svr_profile_enable(svr_context *ctx, int on);
+/* Synchronises the stream, folds all pending event pairs and returns the accumulated device time and
+ * launch count of one kind since the last svr_profile_reset. */
+int svr_profile_read(svr_context *ctx, int kind, double *total_ms, int64_t *launches);
+int svr_profile_reset(svr_context *ctx);
+
 /* ---- pure host helpers (no device work; usable without a GPU) ---------------------------- */
 /* Slice-level EM of irtkReconstruction::EStepGPU, irtkReconstructionGPU.cc:3184-3440.
  * slice_potential[S] in/out (exclusions set to -1), scale[S], slice_weight[S] in/out,

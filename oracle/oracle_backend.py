@@ -1,4 +1,4 @@
-"""Oracle-backed twin of fetalreconstruction_b200.reconstruction.Reconstruction (TESTS ONLY).
+"""Oracle-backed twin of fetalreconstruction_b200.reconstruction.Reconstruction (TEST INFRASTRUCTURE ONLY: tests/, smoke() and bench.py's CPU legs).
 
 Same method set and call semantics as the CUDA-backed class, implemented with oracle/svr_oracle.c on
 numpy arrays.  Used (a) as the checker the CUDA path is compared against through the SAME host
