@@ -181,11 +181,11 @@ int svr_init_reconstruction_volume(svr_context* c, int sx, int sy, int sz, float
     c->vg.vx = sx; c->vg.vy = sy; c->vg.vz = sz;
     if (dev_alloc(c, &c->recon, c->V) || dev_alloc(c, &c->recon_tmp1, c->V) || dev_alloc(c, &c->recon_tmp2, c->V) ||
         dev_alloc(c, &c->volw, c->V) || dev_alloc(c, &c->mask_f, c->V) || dev_alloc(c, &c->mask_u8, c->V) ||
-        dev_alloc(c, &c->acc2, c->V) || dev_alloc(c, &c->pack2, c->V))
+        dev_alloc(c, &c->acc2, c->V + 2) || dev_alloc(c, &c->pack2, c->V))
         return 1;
     SVR_CUDA(c, cudaMemsetAsync(c->recon, 0, c->V * sizeof(float), c->stream));
     SVR_CUDA(c, cudaMemsetAsync(c->volw, 0, c->V * sizeof(float), c->stream));
-    SVR_CUDA(c, cudaMemsetAsync(c->acc2, 0, c->V * sizeof(float2), c->stream));
+    SVR_CUDA(c, cudaMemsetAsync(c->acc2, 0, (c->V + 2) * sizeof(float2), c->stream));
     SVR_CUDA(c, cudaMemsetAsync(c->mask_f, 0, c->V * sizeof(float), c->stream));
     SVR_CUDA(c, cudaMemsetAsync(c->mask_u8, 0, c->V, c->stream));
     c->have_mask = false;

@@ -9,18 +9,20 @@
 #define SVR_STEP 0.0001f       // __step, include/reconstruction_cuda2.cuh:54
 
 // Per-slice geometry, rebuilt on the device whenever the matrices / voxel sizes change
-// (svr_set_slice_matrices, svr_set_slice_dims).  176 bytes, 16-byte aligned.
+// (svr_set_slice_matrices, svr_set_slice_dims).  16-byte aligned.
+//
+// "PSF units": the tap position is carried pre-scaled so that calcPSF (reconstruction_cuda2.cu:112-131)
+// needs no per-tap constant multiplies:
+//   in-plane rows x,y are scaled by  dim * (dim / 2.3548) * pi   -> u = ux^2 + uy^2 = (pi r)^2
+//   the through-plane row z by       dim.z * sqrt(log2(e)/2) / sigma_z, sigma_z = dim.z / 2.3548
+//                                    -> gauss = 2^(-dz^2)
 struct __align__(16) SliceGeom {
     float i2w[12];   // slice image -> world, rows 0..2
     float t[12];     // slice -> volume transform (world), rows 0..2
     float a[12];     // comb = W2I * Tinv * reconI2W, rows 0..2 (reconstruction_cuda2.cu:223)
-    // tap-offset basis in "PSF units": column j of comb scaled per row by
-    //   row x: dim.x * kx   row y: dim.y * ky   row z: dim.z      (cuda2.cu:125-126,158)
-    float bx[3], by[3], bz[3];
-    float kx, ky, kpad;      // dim.x / 2.3548, dim.y / 2.3548 (in-plane scale applied inside calcPSF)
-    float gz;                // -log2(e) / (2 sigma_z^2), sigma_z = dim.z / 2.3548 (cuda2.cu:114,130)
-    float dimx, dimy, dimz;  // slice voxel size
-    float pad0;
+    float bx[3], by[3], bz[3];   // column j of comb in PSF units (tap-offset basis)
+    float kx, ky, kz;            // PSF-unit scale per mm for rows x, y, z
+    float dimx, dimy, dimz;      // slice voxel size
 };
 
 struct VolGeom {
@@ -55,30 +57,30 @@ __device__ __forceinline__ float sin_approx(float x)
     return y;
 }
 
-// sinc^2(pi r) * exp(-dz^2 / (2 sigma_z^2)) with (ux,uy) already in the sinc's units and
-// gz = -log2(e)/(2 sigma_z^2).  Restates calcPSF (reconstruction_cuda2.cu:112-131, USE_SINC_PSF);
-// the reference is built with --use_fast_math, hence the approx MUFU forms.  sinc(0) = 1 (deviation D5).
-__device__ __forceinline__ float psf_eval(float ux, float uy, float dz, float gz)
+// sinc^2(pi r) * exp(-z^2 / (2 sigma_z^2)) for a tap position in PSF units: u = (pi r)^2, gauss = 2^(-dz^2).
+// Restates calcPSF (reconstruction_cuda2.cu:112-131, USE_SINC_PSF); the reference is built with
+// --use_fast_math, hence the approx MUFU forms (rsqrt, sin, ex2: 3 MUFU + 9 FP32 per tap).
+// The 1e-30 keeps rsqrt finite at r == 0, where sin(x)/x evaluates to exactly 1 (deviation D5: the
+// reference computes sin(0)/0 = NaN there).
+__device__ __forceinline__ float psf_eval(float ux, float uy, float dz)
 {
-    const float u = fmaf(ux, ux, uy * uy);
-    const float rinv = rsqrt_approx(u);           // +inf at u == 0
-    const float r = u * rinv;                      // NaN at u == 0
-    const float sn = sin_approx(3.14159265359f * r);
-    float si = sn * (rinv * 0.31830988618f);       // sin(pi r) / (pi r)
-    si = (u > 0.0f) ? si : 1.0f;
-    const float g = ex2_approx(dz * dz * gz);
+    const float u = fmaf(ux, ux, fmaf(uy, uy, 1.0e-30f));
+    const float rinv = rsqrt_approx(u);
+    const float si = sin_approx(u * rinv) * rinv;      // sin(pi r) / (pi r)
+    const float g = ex2_approx(-(dz * dz));
     return si * si * g;
 }
 
 // Per-pixel constants of the tap loop.
 struct PixelSetup {
     int cx, cy, cz;          // rounded volume voxel the pixel centre maps to (cuda2.cu:225-226)
-    float ex, ey, ez;        // PSF-unit offset of that voxel from the pixel: scale*((A c - p)*dim - psf_c)
+    float ex, ey, ez;        // PSF-unit offset of that voxel from the pixel: k * ((A c - p) * dim - psf_c)
+    bool interior;           // the whole 16^3 support lies inside the volume: no clamping, no bounds checks
 };
 
 __device__ __forceinline__ int f2i_clamped(float f)
-{   // round-to-nearest-even is irrelevant here: f is already integer-valued (roundf result)
-    f = fminf(fmaxf(f, -1.0e6f), 1.0e6f);         // NaN -> -1e6 (fmaxf returns the non-NaN operand)
+{   // f is already integer-valued (roundf result); NaN -> -1e6 (fmaxf returns the non-NaN operand)
+    f = fminf(fmaxf(f, -1.0e6f), 1.0e6f);
     return __float2int_rn(f);
 }
 
@@ -94,47 +96,63 @@ __device__ __forceinline__ PixelSetup pixel_setup(const SliceGeom& g, const VolG
     const float3 q = mat_pt(g.a, cc);              // comb * centre voxel -> slice pixel coordinates
     ps.ex = ((q.x - p.x) * g.dimx - vg.psf_c[0]) * g.kx;
     ps.ey = ((q.y - p.y) * g.dimy - vg.psf_c[1]) * g.ky;
-    ps.ez = ((q.z - p.z) * g.dimz - vg.psf_c[2]);
+    ps.ez = ((q.z - p.z) * g.dimz - vg.psf_c[2]) * g.kz;
+    const int lo = SVR_PSF_CENTRE, hi = SVR_PSF_SUPPORT - 1 - SVR_PSF_CENTRE;
+    ps.interior = ps.cx - lo >= 0 && ps.cx + hi < vg.vx && ps.cy - lo >= 0 && ps.cy + hi < vg.vy &&
+                  ps.cz - lo >= 0 && ps.cz + hi < vg.vz;
     return ps;
 }
 
 // The shared tap loop of K1/K2/K3 (reconstruction_cuda2.cu:229-247, 262-288, 372-394, 498-520).
-// Walks the 16^3 support (x innermost) and calls body(psf, voxel_linear_index) for every tap that
-//   (a) survives the epsilon-skip against the last ACCEPTED tap of its x-row (quirks Q1/Q2), and
-//   (b) lies inside the volume after the unsigned saturation of negative coordinates (Q4).
-// Rows whose (clamped) y or z lies outside the volume contribute nothing and are skipped whole:
-// the skip state is per row, so this is exact.
-template <class Body>
-__device__ __forceinline__ void psf_tap_loop(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, Body&& body)
+// Walks the 16^3 support (x innermost, fully unrolled) and calls, per tap,
+//     tap(i, psf, ok, v)      i = ox + 7 (compile-time after unrolling), v = linear voxel index
+// where ok means the tap (a) survives the epsilon-skip against the last ACCEPTED tap of its x-row
+// (quirks Q1/Q2: the first tap of a row is always accepted) and (b) lies inside the volume after the
+// unsigned saturation of negative coordinates (Q4); psf is 0 when !ok.  After each x-row it calls
+//     row_end(v0)             v0 = linear index of the row's first tap (meaningful when INTERIOR).
+// INTERIOR (the whole support inside the volume) drops every clamp and bounds check, so v = v0 + i
+// and the loads / reductions of a row use immediate offsets from one row pointer.  Otherwise rows whose
+// (clamped) y or z lies outside the volume are skipped whole: the skip state is per row, so this is exact.
+template <bool INTERIOR, class Tap, class RowEnd>
+__device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, Tap&& tap,
+                                         RowEnd&& row_end)
 {
     const int vx = vg.vx, vy = vg.vy, vz = vg.vz;
-    const float gz = g.gz;
     const float bx0 = g.bx[0], by0 = g.by[0], bz0 = g.bz[0];
+    const float bx1 = g.bx[1], by1 = g.by[1], bz1 = g.bz[1];
+    const float bx2 = g.bx[2], by2 = g.by[2], bz2 = g.bz[2];
 #pragma unroll 1
     for (int oz = -SVR_PSF_CENTRE; oz <= SVR_PSF_SUPPORT - 1 - SVR_PSF_CENTRE; ++oz) {
-        const int zi = max(ps.cz + oz, 0);
-        if (zi >= vz) continue;
+        const int zi = INTERIOR ? ps.cz + oz : max(ps.cz + oz, 0);
+        if (!INTERIOR && zi >= vz) continue;
         const float foz = (float)oz;
-        const float zx = fmaf(foz, g.bx[2], ps.ex), zy = fmaf(foz, g.by[2], ps.ey), zz = fmaf(foz, g.bz[2], ps.ez);
+        const float zx = fmaf(foz, bx2, ps.ex), zy = fmaf(foz, by2, ps.ey), zz = fmaf(foz, bz2, ps.ez);
 #pragma unroll 1
         for (int oy = -SVR_PSF_CENTRE; oy <= SVR_PSF_SUPPORT - 1 - SVR_PSF_CENTRE; ++oy) {
-            const int yi = max(ps.cy + oy, 0);
-            if (yi >= vy) continue;
+            const int yi = INTERIOR ? ps.cy + oy : max(ps.cy + oy, 0);
+            if (!INTERIOR && yi >= vy) continue;
             const float foy = (float)oy;
-            const float rx = fmaf(foy, g.bx[1], zx), ry = fmaf(foy, g.by[1], zy), rz = fmaf(foy, g.bz[1], zz);
+            const float rx = fmaf(foy, bx1, zx), ry = fmaf(foy, by1, zy), rz = fmaf(foy, bz1, zz);
             const int rowbase = (zi * vy + yi) * vx;
+            const int v0 = rowbase + ps.cx - SVR_PSF_CENTRE;
             float old = FLT_MAX;
 #pragma unroll
-            for (int ox = -SVR_PSF_CENTRE; ox <= SVR_PSF_SUPPORT - 1 - SVR_PSF_CENTRE; ++ox) {
-                const float fox = (float)ox;
-                const float psf = psf_eval(fmaf(fox, bx0, rx), fmaf(fox, by0, ry), fmaf(fox, bz0, rz), gz);
+            for (int i = 0; i < SVR_PSF_SUPPORT; ++i) {
+                const float fox = (float)(i - SVR_PSF_CENTRE);
+                const float psf = psf_eval(fmaf(fox, bx0, rx), fmaf(fox, by0, ry), fmaf(fox, bz0, rz));
                 // abs(oldPSF - psfval) < PSF_EPSILON with a double 1e-5 (cuda2.cu:238): true iff the float
                 // difference is <= 1e-5f (the largest float below the double literal).
-                if (fabsf(old - psf) <= 1.0e-5f) continue;
-                old = psf;
-                const int xi = max(ps.cx + ox, 0);
-                if (xi < vx) body(psf, rowbase + xi);
+                const bool accept = !(fabsf(old - psf) <= 1.0e-5f);
+                old = accept ? psf : old;
+                if (INTERIOR) {
+                    tap(i, accept ? psf : 0.0f, accept, v0 + i);
+                } else {
+                    const int xi = max(ps.cx + i - SVR_PSF_CENTRE, 0);
+                    const bool ok = accept && xi < vx;
+                    tap(i, ok ? psf : 0.0f, ok, rowbase + xi);
+                }
             }
+            row_end(v0);
         }
     }
 }

@@ -345,10 +345,12 @@ __constant__ int c_dirs[13][3] = {
     { 1, -1, 0 }, { 1, 0, 1 }, { 0, 1, 1 }, { 1, 1, 1 }, { 1, -1, 1 }, { 0, 0, 1 } };
 
 __global__ void reg_prep_kernel(size_t V, const float* __restrict__ recon, float2* __restrict__ acc2,
-                                float* __restrict__ post, int adaptive, float alpha, float min_i, float max_i)
+                                const unsigned char* __restrict__ mask, float* __restrict__ post, int adaptive,
+                                float alpha, float min_i, float max_i)
 {
     for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < V; v += (size_t)gridDim.x * blockDim.x) {
         float2 a = acc2[v];
+        if (!mask[v]) a = make_float2(0.f, 0.f);           // the per-tap mask test of cuda2.cu:509-510, applied per voxel
         if (!adaptive && a.y != 0.f) { a.x = a.x / a.y; a.y = 1.0f; }
         acc2[v] = a;
         float r = recon[v] + a.x * alpha;
@@ -415,7 +417,7 @@ reg_kernel(int vx, int vy, int vz, const float* __restrict__ original, const flo
 int svr_launch_regularize(svr_context* c, int adaptive, float alpha, float min_i, float max_i, float delta, float lambda)
 {
     ProfScope prof(c, 3);
-    reg_prep_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->recon, c->acc2, c->recon_tmp1, adaptive, alpha, min_i, max_i);
+    reg_prep_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->recon, c->acc2, c->mask_u8, c->recon_tmp1, adaptive, alpha, min_i, max_i);
     SVR_KERNEL_CHECK(c);
     dim3 block(64, 4, 1), grid(divup_i(c->vx, 64), divup_i(c->vy, 4), c->vz);
     reg_kernel<<<grid, block, 0, c->stream>>>(c->vx, c->vy, c->vz, c->recon, c->recon_tmp1, c->acc2, c->recon_tmp2, delta, alpha, lambda);

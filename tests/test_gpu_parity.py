@@ -24,8 +24,12 @@ from oracle.oracle_backend import OracleReconstruction
 
 pytestmark = pytest.mark.gpu
 
+# Bounds are ~3-5x the deviations measured on B200 (profiles/r01_*_parity_report.json), e.g. v_PSF_sums
+# rms 9e-5 / max 1.6e-2, GaussianReconstruction rms 1.6e-5 / max 2.9e-3, simulated slices rms 8.6e-6 /
+# max 1.2e-3, final volume of the full loop rms 4.6e-5 / max 4.7e-3.  The max bounds are loose because a
+# single flipped epsilon-skip decision moves one pixel's PSF mass by up to a few per cent.
 # volume-level (many-pixel sums)
-VOL_RMS, VOL_MAX = 2e-4, 5e-3
+VOL_RMS, VOL_MAX = 3e-4, 3e-2
 # slice-level
 PIX_RMS, PIX_P999, PIX_MAX = 5e-4, 2e-3, 8e-2
 
@@ -83,7 +87,7 @@ def test_psf_sums_and_voxel_counts(pair):
 
 
 def test_gaussian_reconstruction_volume(pair):
-    check_volume(pair["gpu_volw"], pair["orc_volw"], "volWeights")
+    check_volume(pair["gpu_volw"], pair["orc_volw"], "volWeights", mx=6e-2)
     check_volume(pair["gpu_recon0"], pair["orc_recon0"], "GaussianReconstruction")
     mask = pair["ds"].mask.ravel()
     assert np.all(pair["gpu_recon0"][mask == 0] == 0)
@@ -114,7 +118,7 @@ def test_em_steps_and_superresolution(pair):
     args = (1, sw, False, min(1.0, 0.05 / lam), float(pos.min()), float(pos.max()), delta, lam * delta * delta)
     g.Superresolution(*args); o.Superresolution(*args)
     check_volume(g.debugConfidenceMap(), o.debugConfidenceMap(), "confidence map (normalised)")
-    check_volume(g.debugAddon(), o.debugAddon(), "addon (normalised)", rms=2e-3, mx=5e-2)
+    check_volume(g.debugAddon(), o.debugAddon(), "addon (normalised)", rms=5e-4, mx=6e-2)
     check_volume(g.syncCPU(), o.syncCPU(), "Superresolution volume")
     g.SimulateSlices(); o.SimulateSlices()
     a, b = g.MStep(2, 1e-4, sig_o, 0.9, m), o.MStep(2, 1e-4, sig_o, 0.9, m)

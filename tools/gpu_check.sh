@@ -1,10 +1,17 @@
 #!/bin/bash
-# First-contact GPU script: parity report, gpu tests, a tiny bench, the C3 bench, and an ncu launch list.
+# GPU check: parity report, gpu tests, the C3 bench, and an ncu launch list restricted to our kernels.
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
-nproc >> gpurun_out/gpu_info.txt
-echo "== parity report"; timeout 600 python tools/parity_report.py > gpurun_out/parity_report.txt 2> gpurun_out/parity_report.err; echo "rc=$?"; tail -5 gpurun_out/parity_report.err
-echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.txt 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_gpu.txt
-echo "== bench tiny"; timeout 300 python bench.py --workload tiny --steps 2 --warmup 1 > gpurun_out/bench_tiny.json 2> gpurun_out/bench_tiny.err; echo "rc=$?"; cat gpurun_out/bench_tiny.json | cut -c1-1500; tail -3 gpurun_out/bench_tiny.err
-echo "== bench C3"; timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "rc=$?"; cat gpurun_out/bench_c3.json | cut -c1-3000; tail -3 gpurun_out/bench_c3.err
-echo "== ncu launch list (tiny)"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_tiny.csv python bench.py --workload tiny --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_tiny.log 2>&1; echo "rc=$?"
+KREGEX='regex:(scatter_kernel|simulate_kernel|reg_|estep|mstep|scale_|robust|pack_volume|equalize|init_em|mask_|build_geom|fold_|potential|DeviceSelect|DeviceCompact)'
+echo "== parity report"; timeout 600 python tools/parity_report.py > gpurun_out/parity_report.txt 2> gpurun_out/parity_report.err; echo "rc=$?"; tail -3 gpurun_out/parity_report.err
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.txt 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_gpu.txt
+echo "== bench C3"; timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "rc=$?"; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_c3.json'))
+print('value',d['value'],'ms_per_step',d['ms_per_step'],'vph',d['volumes_per_hour'],'e2e',d['e2e']['value'] if d['e2e'] else None)
+for k,v in d['roofline']['kernels'].items(): print(k, v)
+print(d['cpu_baseline']); print(d['clocks'])
+PY
+tail -3 gpurun_out/bench_c3.err
+if [ "$1" == "ncu" ]; then
+echo "== ncu launch list (C3, one step)"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 200 --csv --log-file gpurun_out/launches_c3.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > gpurun_out/ncu_c3.log 2>&1; echo "rc=$?"
+fi
