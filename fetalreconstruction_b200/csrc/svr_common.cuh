@@ -59,14 +59,16 @@ __device__ __forceinline__ float sin_approx(float x)
 
 // sinc^2(pi r) * exp(-z^2 / (2 sigma_z^2)) for a tap position in PSF units: u = (pi r)^2, gauss = 2^(-dz^2).
 // Restates calcPSF (reconstruction_cuda2.cu:112-131, USE_SINC_PSF); the reference is built with
-// --use_fast_math, hence the approx MUFU forms (rsqrt, sin, ex2: 3 MUFU + 9 FP32 per tap).
-// The 1e-30 keeps rsqrt finite at r == 0, where sin(x)/x evaluates to exactly 1 (deviation D5: the
-// reference computes sin(0)/0 = NaN there).
+// --use_fast_math, hence the approx MUFU forms (rsqrt, sin, ex2: 3 MUFU + ~10 FP32 per tap).
+// sin.approx has an ABSOLUTE error (~2^-21), which sin(x)/x amplifies by 1/x: below x^2 = 1e-3 the
+// two-term series 1 - x^2/6 (error < 1e-8) is used instead.  It also covers x == 0, where the
+// reference evaluates sin(0)/0 = NaN (deviation D5).
 __device__ __forceinline__ float psf_eval(float ux, float uy, float dz)
 {
-    const float u = fmaf(ux, ux, fmaf(uy, uy, 1.0e-30f));
+    const float u = fmaf(ux, ux, uy * uy);
     const float rinv = rsqrt_approx(u);
-    const float si = sin_approx(u * rinv) * rinv;      // sin(pi r) / (pi r)
+    float si = sin_approx(u * rinv) * rinv;            // sin(pi r) / (pi r)
+    si = (u < 1.0e-3f) ? fmaf(u, -0.16666667f, 1.0f) : si;
     const float g = ex2_approx(-(dz * dz));
     return si * si * g;
 }
