@@ -9,7 +9,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libsvr_b200.so")
+LIB_PATH = os.environ.get("SVR_B200_LIB", os.path.join(HERE, "csrc", "libsvr_b200.so"))
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "svr_abi.h")
 
 _lib = None

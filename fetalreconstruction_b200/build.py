@@ -44,7 +44,9 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    out = os.environ.get("SVR_B200_LIB_OUT", LIB)       # experiments: build variants side by side
+    extra = os.environ.get("SVR_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     env = dict(os.environ)
     # the image's $CC/$CXX wrappers are not a usable nvcc host compiler; use the system g++
     env.pop("CC", None)
@@ -58,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + log[-4000:])
     if verbose:
         print(log)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

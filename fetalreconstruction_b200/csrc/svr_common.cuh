@@ -23,6 +23,10 @@ struct __align__(16) SliceGeom {
     float bx[3], by[3], bz[3];   // column j of comb in PSF units (tap-offset basis)
     float kx, ky, kz;            // PSF-unit scale per mm for rows x, y, z
     float dimx, dimy, dimz;      // slice voxel size
+    // Gaussian forward differencing along an x-row (dz_i = dz_0 + i*bz0): g_{i+1} = g_i * rho_i,
+    // rho_{i+1} = rho_i * kappa with rho_i = 2^-(2 dz_i bz0 + bz0^2), kappa = 2^-(2 bz0^2).
+    float two_b, bb, kappa;
+    int recur;                   // 1 when the recurrence cannot overflow (|bz0| <= 1, |bz0|+|bz1|+|bz2| <= 4)
 };
 
 struct VolGeom {
@@ -59,18 +63,17 @@ __device__ __forceinline__ float sin_approx(float x)
 
 // sinc^2(pi r) * exp(-z^2 / (2 sigma_z^2)) for a tap position in PSF units: u = (pi r)^2, gauss = 2^(-dz^2).
 // Restates calcPSF (reconstruction_cuda2.cu:112-131, USE_SINC_PSF); the reference is built with
-// --use_fast_math, hence the approx MUFU forms (rsqrt, sin, ex2: 3 MUFU + ~10 FP32 per tap).
+// --use_fast_math, hence the approx MUFU forms (rsqrt, sin for the sinc; ex2 for the Gaussian).
 // sin.approx has an ABSOLUTE error (~2^-21), which sin(x)/x amplifies by 1/x: below x^2 = 1e-3 the
 // two-term series 1 - x^2/6 (error < 1e-8) is used instead.  It also covers x == 0, where the
 // reference evaluates sin(0)/0 = NaN (deviation D5).
-__device__ __forceinline__ float psf_eval(float ux, float uy, float dz)
+__device__ __forceinline__ float sinc2_eval(float ux, float uy)
 {
     const float u = fmaf(ux, ux, uy * uy);
     const float rinv = rsqrt_approx(u);
     float si = sin_approx(u * rinv) * rinv;            // sin(pi r) / (pi r)
     si = (u < 1.0e-3f) ? fmaf(u, -0.16666667f, 1.0f) : si;
-    const float g = ex2_approx(-(dz * dz));
-    return si * si * g;
+    return si * si;
 }
 
 // Per-pixel constants of the tap loop.
@@ -115,7 +118,12 @@ __device__ __forceinline__ PixelSetup pixel_setup(const SliceGeom& g, const VolG
 // INTERIOR (the whole support inside the volume) drops every clamp and bounds check, so v = v0 + i
 // and the loads / reductions of a row use immediate offsets from one row pointer.  Otherwise rows whose
 // (clamped) y or z lies outside the volume are skipped whole: the skip state is per row, so this is exact.
-template <bool INTERIOR, class Tap, class RowEnd>
+//
+// RECUR evaluates the through-plane Gaussian of a row by forward differencing in two segments of 8 taps
+// (2 ex2 per segment instead of 1 per tap: the MUFU unit is the busiest pipe of these kernels); the
+// accumulated rounding (<= ~2.5e-6 relative after 7 steps) is of the size of the ex2.approx argument
+// rounding of the direct form.  Slices with extreme through-plane scaling use the direct form.
+template <bool INTERIOR, bool RECUR, class Tap, class RowEnd>
 __device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, Tap&& tap,
                                          RowEnd&& row_end)
 {
@@ -123,6 +131,8 @@ __device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, 
     const float bx0 = g.bx[0], by0 = g.by[0], bz0 = g.bz[0];
     const float bx1 = g.bx[1], by1 = g.by[1], bz1 = g.bz[1];
     const float bx2 = g.bx[2], by2 = g.by[2], bz2 = g.bz[2];
+    const float two_b = g.two_b, bb = g.bb, kappa = g.kappa;
+    constexpr int HALF = SVR_PSF_SUPPORT / 2;
 #pragma unroll 1
     for (int oz = -SVR_PSF_CENTRE; oz <= SVR_PSF_SUPPORT - 1 - SVR_PSF_CENTRE; ++oz) {
         const int zi = INTERIOR ? ps.cz + oz : max(ps.cz + oz, 0);
@@ -138,10 +148,24 @@ __device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, 
             const int rowbase = (zi * vy + yi) * vx;
             const int v0 = rowbase + ps.cx - SVR_PSF_CENTRE;
             float old = FLT_MAX;
+            float gz = 0.f, rho = 0.f;
 #pragma unroll
             for (int i = 0; i < SVR_PSF_SUPPORT; ++i) {
                 const float fox = (float)(i - SVR_PSF_CENTRE);
-                const float psf = psf_eval(fmaf(fox, bx0, rx), fmaf(fox, by0, ry), fmaf(fox, bz0, rz));
+                float gauss;
+                if (RECUR) {
+                    if (i % HALF == 0) {                  // (re)start a segment with direct evaluations
+                        const float dz = fmaf(fox, bz0, rz);
+                        gz = ex2_approx(-(dz * dz));
+                        rho = ex2_approx(-fmaf(two_b, dz, bb));
+                    }
+                    gauss = gz;
+                    if (i % HALF != HALF - 1) { gz *= rho; rho *= kappa; }
+                } else {
+                    const float dz = fmaf(fox, bz0, rz);
+                    gauss = ex2_approx(-(dz * dz));
+                }
+                const float psf = sinc2_eval(fmaf(fox, bx0, rx), fmaf(fox, by0, ry)) * gauss;
                 // abs(oldPSF - psfval) < PSF_EPSILON with a double 1e-5 (cuda2.cu:238): true iff the float
                 // difference is <= 1e-5f (the largest float below the double literal).
                 const bool accept = !(fabsf(old - psf) <= 1.0e-5f);
@@ -156,6 +180,20 @@ __device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, 
             }
             row_end(v0);
         }
+    }
+}
+
+// Dispatch on the (per-thread) interior flag and the (per-slice) recurrence flag.
+template <class Tap, class RowEnd>
+__device__ __forceinline__ void psf_rows_dispatch(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, Tap&& tap,
+                                                  RowEnd&& row_end)
+{
+    if (g.recur) {
+        if (ps.interior) psf_rows<true, true>(g, vg, ps, tap, row_end);
+        else psf_rows<false, true>(g, vg, ps, tap, row_end);
+    } else {
+        if (ps.interior) psf_rows<true, false>(g, vg, ps, tap, row_end);
+        else psf_rows<false, false>(g, vg, ps, tap, row_end);
     }
 }
 

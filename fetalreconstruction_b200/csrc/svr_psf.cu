@@ -19,6 +19,11 @@
 // Reference kernels restated here: reconstruction_cuda2.cu:176-295 (K1), 298-404 (K2), 408-522 (K3).
 #include "svr_context.h"
 
+// Resident CTAs per SM the PSF kernels are compiled for (register budget = 65536 / (128 * SVR_MINB)).
+#ifndef SVR_MINB
+#define SVR_MINB 5
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Per-slice geometry (runs when matrices or voxel sizes change; S threads).
 // comb = (W2I * Tinv) * reconI2W in float, product order of reconstruction_cuda2.cu:223.
@@ -53,6 +58,10 @@ __global__ void build_geom_kernel(int S, const float* __restrict__ T, const floa
         g.by[j] = comb[4 + j] * dy * g.ky;
         g.bz[j] = comb[8 + j] * dz * g.kz;
     }
+    g.two_b = 2.0f * g.bz[0];
+    g.bb = g.bz[0] * g.bz[0];
+    g.kappa = exp2f(-2.0f * g.bb);
+    g.recur = (fabsf(g.bz[0]) <= 1.0f && fabsf(g.bz[0]) + fabsf(g.bz[1]) + fabsf(g.bz[2]) <= 4.0f) ? 1 : 0;
     out[k] = g;
 }
 
@@ -95,7 +104,7 @@ __device__ __forceinline__ void red_row_paired(float2* __restrict__ acc2, int v0
 // K1: gaussianReconstructionKernel3D_tex (reconstruction_cuda2.cu:176-295).
 // Pass 1: sume = sum of accepted in-volume taps (mask ignored, quirk Q3); stored only if > 0.5.
 // Pass 2: scatter psf/sume * {s*scale, 1}; flag the pixel if any accepted tap landed on a masked voxel.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SVR_MINB)
 gaussian_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
                         const float* __restrict__ slices, const float* __restrict__ scales,
                         const SliceGeom* __restrict__ geom, VolGeom vg, const unsigned char* __restrict__ mask,
@@ -112,10 +121,7 @@ gaussian_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx
     const PixelSetup ps = pixel_setup(g, vg, x, y);
 
     float sume = 0.f;
-    if (ps.interior)
-        psf_rows<true>(g, vg, ps, [&](int, float psf, bool, int) { sume += psf; }, [](int) {});
-    else
-        psf_rows<false>(g, vg, ps, [&](int, float psf, bool, int) { sume += psf; }, [](int) {});
+    psf_rows_dispatch(g, vg, ps, [&](int, float psf, bool, int) { sume += psf; }, [](int) {});
     if (!(sume > 0.5f)) return;
     psf_sums[idx] = sume;
 
@@ -124,11 +130,12 @@ gaussian_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx
     bool any = false;
     if (ps.interior) {
         float p[SVR_PSF_SUPPORT];
-        psf_rows<true>(g, vg, ps,
-            [&](int i, float psf, bool ok, int v) { p[i] = psf; if (ok && mask[v]) any = true; },
-            [&](int v0) { red_row_paired(acc2, v0, p, sv, inv); });
+        auto tap = [&](int i, float psf, bool ok, int v) { p[i] = psf; if (ok && mask[v]) any = true; };
+        auto row = [&](int v0) { red_row_paired(acc2, v0, p, sv, inv); };
+        if (g.recur) psf_rows<true, true>(g, vg, ps, tap, row);
+        else psf_rows<true, false>(g, vg, ps, tap, row);
     } else {
-        psf_rows<false>(g, vg, ps,
+        psf_rows_dispatch(g, vg, ps,
             [&](int, float psf, bool ok, int v) {
                 if (ok) {
                     atomicAdd(&acc2[v], make_float2(psf * sv, psf * inv));
@@ -157,7 +164,7 @@ int svr_launch_gaussian_scatter(svr_context* c)
 // ---------------------------------------------------------------------------------------------
 // K2: simulateSlicesKernel3D_tex (reconstruction_cuda2.cu:298-404).
 // pack2[v] = {recon[v]*m, m} with m = (mask != 0), so a tap is one predicated 64-bit load + 2 FFMA.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SVR_MINB)
 simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
                 const SliceGeom* __restrict__ geom, VolGeom vg, const float2* __restrict__ pack2,
                 const float* __restrict__ psf_sums, float* __restrict__ simslices, float* __restrict__ simweights,
@@ -181,8 +188,7 @@ simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx
             wsum = fmaf(psf, pm.y, wsum);
         }
     };
-    if (ps.interior) psf_rows<true>(g, vg, ps, tap, [](int) {});
-    else psf_rows<false>(g, vg, ps, tap, [](int) {});
+    psf_rows_dispatch(g, vg, ps, tap, [](int) {});
     const float weight = wsum / sume;
     if (weight > 0.f) {
         simslices[idx] = sim / wsum;              // (sum psf/sume * x) / (sum psf/sume)
@@ -205,7 +211,7 @@ int svr_launch_simulate(svr_context* c)
 
 // ---------------------------------------------------------------------------------------------
 // K3: SuperresolutionKernel3D_tex (reconstruction_cuda2.cu:408-522).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SVR_MINB)
 superres_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
                         const float* __restrict__ slices, const float* __restrict__ weights,
                         const float* __restrict__ simslices, const float* __restrict__ slice_weights,
@@ -232,10 +238,12 @@ superres_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx
     const PixelSetup ps = pixel_setup(g, vg, x, y);
     if (ps.interior) {
         float p[SVR_PSF_SUPPORT];
-        psf_rows<true>(g, vg, ps, [&](int i, float psf, bool, int) { p[i] = psf; },
-                       [&](int v0) { red_row_paired(acc2, v0, p, aw, cw); });
+        auto tap = [&](int i, float psf, bool, int) { p[i] = psf; };
+        auto row = [&](int v0) { red_row_paired(acc2, v0, p, aw, cw); };
+        if (g.recur) psf_rows<true, true>(g, vg, ps, tap, row);
+        else psf_rows<true, false>(g, vg, ps, tap, row);
     } else {
-        psf_rows<false>(g, vg, ps,
+        psf_rows_dispatch(g, vg, ps,
             [&](int, float psf, bool ok, int v) { if (ok) atomicAdd(&acc2[v], make_float2(psf * aw, psf * cw)); },
             [](int) {});
     }
