@@ -65,6 +65,15 @@ _SIGNATURES = {
     "svr_profile_enable": (ip, [vp, ip]),
     "svr_profile_read": (ip, [vp, ip, D, C.POINTER(C.c_int64)]),
     "svr_profile_reset": (ip, [vp]),
+    "svr_reg_init_storage": (ip, [vp, ip, ip, ip, fp, fp, fp]),
+    "svr_reg_fill_slices": (ip, [vp, vp, vp]),
+    "svr_reg_update_slices_i2w": (ip, [vp, vp]),
+    "svr_reg_prepare": (ip, [vp]),
+    "svr_reg_set_schedule": (ip, [vp, ip, ip, ip]),
+    "svr_reg_register": (ip, [vp, vp]),
+    "svr_reg_evaluate": (ip, [vp, vp, ip, vp]),
+    "svr_reg_evaluations": (C.c_int64, [vp]),
+    "svr_reg_debug_get": (ip, [vp, ip, vp]),
     "svr_host_slice_em": (ip, [ip, vp, vp, vp, vp, ip, vp, ip, dp, vp]),
     "svr_host_small_slices": (ip, [ip, vp, vp, I]),
     "svr_host_partition": (ip, [ip, vp, ip, ip, I, I]),

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libsvr_b200.so")
-SOURCES = ["svr_abi.cu", "svr_psf.cu", "svr_em.cu"]
+SOURCES = ["svr_abi.cu", "svr_psf.cu", "svr_em.cu", "svr_reg.cu"]
 HEADERS = ["svr_common.cuh", "svr_context.h", os.path.join("..", "..", "include", "svr_abi.h")]
 
 NVCC_FLAGS = [

@@ -72,7 +72,10 @@ struct svr_context {
     float recon_i2w[16]{}, recon_w2i[16]{};
     float quality_factor = 1.0f;
     int sm_count = 148;
+    void* reg = nullptr;           // RegState (svr_reg.cu), owned
+    void* pvr = nullptr;           // PvrState (pvr.cu), owned
 };
+void svr_reg_free(svr_context* c);
 
 // error helper used by every translation unit
 int svr_fail(svr_context* ctx, const char* what, cudaError_t e, const char* file, int line);

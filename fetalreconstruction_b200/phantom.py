@@ -66,6 +66,8 @@ class Dataset:
     psf_c: np.ndarray              # float32 [3]
     min_intensity: float
     max_intensity: float
+    slice_attrs: list | None = None    # ImageAttributes of every slice (for the registration front-end)
+    true_trans: np.ndarray | None = None   # the motion each slice was acquired with [S,16]
 
     @property
     def S(self) -> int:
@@ -132,6 +134,8 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
     trans_inv = np.empty((S, 16), np.float32)
     dims = np.empty((S, 3), np.float32)
     stack_index = np.empty(S, np.int32)
+    slice_attrs = []
+    true_trans = np.empty((S, 16), np.float32)
 
     py, px = torch.meshgrid(torch.arange(Ny, device=dev), torch.arange(Nx, device=dev), indexing="ij")
     pix = torch.stack([px, py, torch.zeros_like(px)], -1).to(torch.float32)
@@ -180,10 +184,12 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
             trans_inv[k] = np.linalg.inv(T_used).astype(np.float32).ravel()
             dims[k] = (cfg.inplane, cfg.inplane, thickness)
             stack_index[k] = st
+            slice_attrs.append(sa)
+            true_trans[k] = T_true.astype(np.float32).ravel()
             k += 1
 
     pos = slices[slices > 0]
     return Dataset(cfg, vol_attr, ri2w.astype(np.float32).ravel(), rw2i.astype(np.float32).ravel(),
                    mask.cpu().numpy(), truth.cpu().numpy(), slices, i2w, w2i, trans, trans_inv, dims,
                    stack_index, psf_centre_offset(cfg.vol_voxel),
-                   float(pos.min()) if pos.size else 0.0, float(pos.max()) if pos.size else 0.0)
+                   float(pos.min()) if pos.size else 0.0, float(pos.max()) if pos.size else 0.0, slice_attrs, true_trans)

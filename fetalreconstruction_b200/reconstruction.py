@@ -79,7 +79,7 @@ class Reconstruction:
     def launch_count(self) -> int:
         return int(self._lib.svr_launch_count(self._h))
 
-    KERNEL_KINDS = ("gaussian", "simulate", "superres", "regularize", "em")
+    KERNEL_KINDS = ("gaussian", "simulate", "superres", "regularize", "em", "reg_eval")
 
     def profile_enable(self, on: bool = True):
         self._ck(self._lib.svr_profile_enable(self._h, int(on)))
@@ -215,6 +215,49 @@ class Reconstruction:
         f = _f32(stack_factors)
         i = np.ascontiguousarray(stack_index, np.int32)
         self._ck(self._lib.svr_restore_slice_intensities(self._h, _p(f), int(f.size), _p(i)))
+
+    # -- slice-to-volume registration (--useGPUReg), reconstruction_cuda2.cuh:326-338 ------------
+    def initRegStorageVolumes(self, size, dim):
+        W, H, S = (int(v) for v in size)
+        self._ck(self._lib.svr_reg_init_storage(self._h, W, H, S, float(dim[0]), float(dim[1]), float(dim[2])))
+        self.regW, self.regH, self.regS = W, H, S
+
+    def FillRegSlices(self, sdata, slices_resampledI2W=None):
+        cube = _f32(np.asarray(sdata).ravel(), (self.regW * self.regH * self.regS,))
+        m = None if slices_resampledI2W is None else _f32(slices_resampledI2W, (self.regS, 16))
+        self._ck(self._lib.svr_reg_fill_slices(self._h, _p(cube), _p(m)))
+
+    def updateResampledSlicesI2W(self, ofsSlice):
+        m = _f32(ofsSlice, (self.regS, 16))
+        self._ck(self._lib.svr_reg_update_slices_i2w(self._h, _p(m)))
+
+    def prepareSliceToVolumeReg(self):
+        self._ck(self._lib.svr_reg_prepare(self._h))
+
+    def setRegSchedule(self, n_levels=2, n_steps=4, n_iterations=20):
+        self._ck(self._lib.svr_reg_set_schedule(self._h, int(n_levels), int(n_steps), int(n_iterations)))
+
+    def registerSlicesToVolume(self, transf):
+        """transf [S,16] -> registered [S,16] (the reference updates its argument in place)."""
+        t = _f32(transf, (self.regS, 16)).copy()
+        self._ck(self._lib.svr_reg_register(self._h, _p(t)))
+        return t
+
+    def evaluateCostsMultipleSlices(self, transf, level=0):
+        """Similarity of every slice for the given transforms (all slices active)."""
+        t = _f32(transf, (self.regS, 16))
+        out = np.zeros(max(self.regS, 1), np.float32)
+        self._ck(self._lib.svr_reg_evaluate(self._h, _p(t), int(level), _p(out)))
+        return out[:self.regS]
+
+    @property
+    def reg_evaluations(self) -> int:
+        return int(self._lib.svr_reg_evaluations(self._h))
+
+    def debugRegSlices(self, blurred=False):
+        out = np.empty(max(self.regW * self.regH * self.regS, 1), np.float32)
+        self._ck(self._lib.svr_reg_debug_get(self._h, 1 if blurred else 0, _p(out)))
+        return out[:self.regW * self.regH * self.regS].reshape(self.regS, self.regH, self.regW)
 
     # -- downloads ------------------------------------------------------------------------------
     def syncCPU(self):

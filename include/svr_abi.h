@@ -111,6 +111,38 @@ int svr_scale_volume(svr_context *ctx, float *scale_out);
  * As in the reference this rescales the restore-copy of the slices (v_slices), not the working set. */
 int svr_restore_slice_intensities(svr_context *ctx, const float *stack_factors, int n_stacks, const int *stack_index);
 
+/* ---- slice-to-volume registration (--useGPUReg) ------------------------------------------
+ * Batched 6-DOF rigid registration of every slice to the current volume, maximising the blurred NCC
+ * summed over three in-slice offsets by finite-difference gradient ascent (2 levels x 4 step sizes x
+ * <= 20 iterations).  The similarity and the optimiser reproduce the reference literally (DESIGN.md
+ * section 6 lists the quirks G1-G4 that are part of the reference's numbers). */
+/* ref: initRegStorageVolumes(uint3 size, float3 dim) .cuh:326, cuda2.cu:4892-5018.  W x H = padded size of the
+ * slices resampled to the volume resolution, S slices; dim = their voxel size. */
+int svr_reg_init_storage(svr_context *ctx, int W, int H, int S, float dx, float dy, float dz);
+/* ref: FillRegSlices(float* sdata, vector<Matrix4> slices_resampledI2W) .cuh:328, cuda2.cu:5023-5088.
+ * cube = float[S][H][W], -1 = padding.  The matrices are stored but, as in the reference, not used. */
+int svr_reg_fill_slices(svr_context *ctx, const float *cube, const float *slices_resampled_i2w /* [S][16] or NULL */);
+/* ref: updateResampledSlicesI2W(vector<Matrix4> ofsSlice) .cuh:330, cuda2.cu:4707-4757: image-to-world of
+ * the resampled slices with their origin reset to 0 (irtkReconstructionGPU.cc:2226-2250). */
+int svr_reg_update_slices_i2w(svr_context *ctx, const float *ofs_slice /* [S][16] */);
+/* ref: prepareSliceToVolumeReg() .cuh:332, cuda2.cu:3800-3959: snapshots the current volume for sampling and
+ * sets levels = 2, steps = 4, iterations = 20, epsilon = 1e-4, blurring = voxel/2 * 2^level, step = 0.1 * 2^level. */
+int svr_reg_prepare(svr_context *ctx);
+/* Overrides the schedule set by svr_reg_prepare (tests; the reference hard-codes it at cuda2.cu:3884-3887). */
+int svr_reg_set_schedule(svr_context *ctx, int n_levels, int n_steps, int n_iterations);
+/* ref: registerSlicesToVolume(vector<Matrix4>& transf_) .cuh:338, cuda2.cu:4760-4867 -> registerMultipleSlicesToVolume
+ * cuda2.cu:4001-4141.  transforms [S][16] in/out (slice -> world transform times the origin offset,
+ * irtkReconstructionGPU.cc:2243-2247). */
+int svr_reg_register(svr_context *ctx, float *transforms);
+/* ref: evaluateCostsMultipleSlices(...) cuda2.cu:4150-4221 with all slices active: similarity[S] of the given
+ * transforms at `level` (0 = fine).  This is the "registration similarity kernel" of BASELINE.json config 5. */
+int svr_reg_evaluate(svr_context *ctx, const float *transforms, int level, float *similarity);
+/* Number of (slice, in-slice offset) cost evaluations of the last svr_reg_register / svr_reg_evaluate call. */
+int64_t svr_reg_evaluations(const svr_context *ctx);
+/* Debug taps: 0 = resampled slices float[S*H*W], 1 = blurred slices of the last level, 2 = similarities
+ * float[5*S], 3 = gradient float[7*S].  ref: getRegSlicesVol_debug / debugRegSlicesVolume .cuh:198-205 */
+int svr_reg_debug_get(svr_context *ctx, int kind, void *out);
+
 /* ---- downloads -------------------------------------------------------------------------- */
 /* ref: syncCPU(float* reconstructed) .cuh:213, cuda2.cu:2031-2037 */
 int svr_sync_cpu(svr_context *ctx, float *reconstructed);
@@ -173,7 +205,8 @@ enum svr_kernel_kind {
     SVR_K_SUPERRES = 2,   /* K3  superres_scatter_kernel  */
     SVR_K_REGULARIZE = 3, /* K4+K5                        */
     SVR_K_EM = 4,         /* E-step, M-step, scale, robust-init reductions */
-    SVR_K_COUNT = 5
+    SVR_K_REG_EVAL = 5,   /* reg_eval_kernel: fused sample + blur + NCC moments of the registration */
+    SVR_K_COUNT = 6
 };
 /* When enabled every launch of the kinds above is bracketed by a cudaEvent pair (no host sync). */
 int svr_profile_enable(svr_context *ctx, int on);

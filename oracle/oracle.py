@@ -39,8 +39,9 @@ class _Geom(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(
-            os.path.join(_HERE, "svr_oracle.c")):
+    srcs = [os.path.join(_HERE, f) for f in ("svr_oracle.c", "reg_oracle.c", "pvr_oracle.c", "Makefile")]
+    newest = max(os.path.getmtime(f) for f in srcs if os.path.exists(f))
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.run(["make", "-C", _HERE, "clean", "all"], check=True, capture_output=True)
     return _LIB_PATH
 
@@ -189,6 +190,50 @@ def host_slice_em(slice_potential, scale, slice_weight, force_excluded, small_sl
     sm = np.ascontiguousarray(small_slices, np.int32)
     lib().orc_host_slice_em(C.c_int(slice_potential.size), _ptr(slice_potential), _ptr(scale), _ptr(slice_weight),
                             _ptr(fe), C.c_int(fe.size), _ptr(sm), C.c_int(sm.size), C.c_double(step), _ptr(state5))
+
+
+# ---- registration (oracle/reg_oracle.c) -------------------------------------------------------------
+def reg_gauss_kernel(sigma):
+    half = np.zeros(32, np.float32)
+    lib().reg_gauss_kernel.restype = C.c_int
+    k = lib().reg_gauss_kernel(C.c_float(sigma), _ptr(half))
+    return int(k), half[:(k + 1) // 2].copy()
+
+
+def reg_filter_gauss_stack(stack, sigma):
+    """stack [n, H, W] float32, filtered in place (FilterGaussStack)."""
+    n, H, W = stack.shape
+    lib().reg_filter_gauss_stack(_ptr(stack), C.c_int(W), C.c_int(H), C.c_int(n), C.c_float(sigma))
+    return stack
+
+
+def reg_tex3d(vol, pos):
+    vz, vy, vx = vol.shape
+    lib().reg_tex3d.restype = C.c_float
+    return float(lib().reg_tex3d(_ptr(vol), vx, vy, vz, C.c_float(pos[0]), C.c_float(pos[1]), C.c_float(pos[2])))
+
+
+def reg_evaluate(resampled, ofs, vol, voxel, recon_w2i, transforms, level):
+    S, H, W = resampled.shape
+    vz, vy, vx = vol.shape
+    sim = np.zeros(max(S, 1), np.float32)
+    ofs = np.ascontiguousarray(ofs, np.float32); tr = np.ascontiguousarray(transforms, np.float32)
+    rw = np.ascontiguousarray(recon_w2i, np.float32)
+    lib().reg_evaluate(W, H, S, _ptr(resampled), _ptr(ofs), _ptr(vol), vx, vy, vz, C.c_float(voxel), _ptr(rw), _ptr(tr),
+                       C.c_int(level), _ptr(sim))
+    return sim[:S]
+
+
+def reg_register_slices(resampled, ofs, vol, voxel, recon_w2i, transforms, n_levels=2, n_steps=4, n_iterations=20):
+    S, H, W = resampled.shape
+    vz, vy, vx = vol.shape
+    ofs = np.ascontiguousarray(ofs, np.float32)
+    tr = np.array(transforms, np.float32, copy=True)
+    rw = np.ascontiguousarray(recon_w2i, np.float32)
+    lib().reg_register_slices.restype = C.c_longlong
+    ev = lib().reg_register_slices(W, H, S, _ptr(resampled), _ptr(ofs), _ptr(vol), vx, vy, vz, C.c_float(voxel), _ptr(rw),
+                                   _ptr(tr), C.c_int(n_levels), C.c_int(n_steps), C.c_int(n_iterations))
+    return tr, int(ev)
 
 
 def num_threads():

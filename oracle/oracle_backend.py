@@ -33,6 +33,7 @@ class OracleReconstruction:
     # uploads
     def InitReconstructionVolume(self, size, dim, data=None, sigma_bias=0.0):
         self.vol_shape = tuple(int(v) for v in size)
+        self.reg_voxel = float(dim[0])
         self.recon = np.zeros(self.V, np.float32) if data is None else np.array(data, np.float32).ravel()
         self.volw = np.zeros(self.V, np.float32)
         self.addon = np.zeros(self.V, np.float32)
@@ -188,6 +189,35 @@ class OracleReconstruction:
         sc = float(np.float32(s2[0] / s2[1]))
         self.scale_volume_apply(sc)
         return sc
+
+    # registration (oracle/reg_oracle.c)
+    def initRegStorageVolumes(self, size, dim):
+        self.regW, self.regH, self.regS = (int(v) for v in size)
+        self.reg_schedule = (2, 4, 20)
+        self.reg_evaluations = 0
+
+    def FillRegSlices(self, sdata, slices_resampledI2W=None):
+        self.reg_slices = np.array(sdata, np.float32).reshape(self.regS, self.regH, self.regW)
+
+    def updateResampledSlicesI2W(self, ofsSlice):
+        self.reg_ofs = np.ascontiguousarray(ofsSlice, np.float32)
+
+    def prepareSliceToVolumeReg(self):
+        vx, vy, vz = self.vol_shape
+        self.reg_vol = self.recon.reshape(vz, vy, vx).copy()
+        self.reg_schedule = (2, 4, 20)
+
+    def setRegSchedule(self, n_levels=2, n_steps=4, n_iterations=20):
+        self.reg_schedule = (n_levels, n_steps, n_iterations)
+
+    def registerSlicesToVolume(self, transf):
+        out, ev = orc.reg_register_slices(self.reg_slices, self.reg_ofs, self.reg_vol, self.reg_voxel, self.recon_w2i,
+                                          transf, *self.reg_schedule)
+        self.reg_evaluations = ev
+        return out
+
+    def evaluateCostsMultipleSlices(self, transf, level=0):
+        return orc.reg_evaluate(self.reg_slices, self.reg_ofs, self.reg_vol, self.reg_voxel, self.recon_w2i, transf, level)
 
     def syncCPU(self):
         return self.recon.copy()

@@ -1,0 +1,106 @@
+"""GPU: the fused registration path (svr_reg.cu through the C ABI) against oracle/reg_oracle.c.
+
+Tolerances.  The similarity is a ratio of mean-subtracted sums over ~1e3-1e4 pixels; the CUDA path forms the
+sums from double raw moments, the oracle from float products accumulated in double: |d similarity| <= 2e-5 is
+asserted (measured ~1e-6).  The optimiser takes discrete decisions on similarity differences against
+epsilon = 1e-4, so a transform can leave the oracle's trajectory when a comparison sits within rounding of
+the threshold; final transforms are therefore compared per parameter with a bulk bound (>= 90 % of the
+slices within 1e-3 mm / degrees) plus a loose bound on the rest, and the similarity-evaluation counts must
+agree within 10 %.
+"""
+import numpy as np
+import pytest
+
+from fetalreconstruction_b200.geometry import rigid_matrix, rigid_parameters
+from fetalreconstruction_b200.phantom import make_dataset, small_config
+from fetalreconstruction_b200.registration import RegistrationFrontEnd
+from oracle.oracle_backend import OracleReconstruction
+
+pytestmark = pytest.mark.gpu
+
+
+def _backends():
+    import torch
+    assert torch.cuda.is_available()
+    from fetalreconstruction_b200.reconstruction import Reconstruction
+    return Reconstruction(0), OracleReconstruction()
+
+
+def _setup(seed=5, vol=36, n_stacks=3, slices=6, size=30, inplane=1.0, spacing=2.0):
+    cfg = small_config(seed=seed, vol=vol, n_stacks=n_stacks, slices=slices, size=size, inplane=inplane, spacing=spacing)
+    cfg.noise = 2.0
+    cfg.corrupt_fraction = 0.0
+    ds = make_dataset(cfg)
+    vx, vy, vz = cfg.vol_size
+    volume = np.where(ds.mask > 0, ds.truth, -1.0).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    pert = np.stack([(ds.true_trans[k].reshape(4, 4).astype(np.float64)
+                      @ rigid_matrix(*rng.normal(0, 0.6, 3), *rng.normal(0, 0.6, 3))).ravel() for k in range(ds.S)])
+    out = []
+    for b in _backends():
+        b.InitReconstructionVolume((vx, vy, vz), (cfg.vol_voxel,) * 3, volume.ravel())
+        b.setMask((vx, vy, vz), (cfg.vol_voxel,) * 3, ds.mask.ravel())
+        if isinstance(b, OracleReconstruction):
+            b.recon_w2i = ds.recon_w2i
+        else:
+            b.initStorageVolumes((ds.slices.shape[2], ds.slices.shape[1], ds.S))
+            b.setSliceDims(ds.dims)
+            b.SetSliceMatrices(ds.trans, ds.trans_inv, ds.i2w, ds.w2i, ds.i2w, ds.w2i, ds.recon_i2w, ds.recon_w2i)
+        fe = RegistrationFrontEnd(b, ds.slices, ds.slice_attrs, cfg.vol_voxel)
+        b.updateResampledSlicesI2W(fe.ofs)
+        b.prepareSliceToVolumeReg()
+        out.append((b, fe))
+    return ds, pert, out
+
+
+@pytest.mark.parametrize("inplane", [1.0, 1.3])
+def test_similarity_matches_oracle(inplane):
+    ds, pert, ((g, feg), (o, feo)) = _setup(inplane=inplane)
+    assert np.array_equal(feg.cube, feo.cube)
+    for level in (0, 1):
+        for tr in (ds.true_trans, pert):
+            t = feg.pack_transforms(tr)
+            sg = g.evaluateCostsMultipleSlices(t, level)
+            so = o.evaluateCostsMultipleSlices(t, level)
+            assert np.abs(sg - so).max() <= 2e-5, (level, np.abs(sg - so).max())
+            assert np.abs(so).max() > 0.3
+    # the per-level blur of the input slices
+    bl = g.debugRegSlices(blurred=True)
+    from oracle import oracle as orc
+    ref = orc.reg_filter_gauss_stack(feo.cube.copy(), ds.cfg.vol_voxel / 2 * 2)
+    assert np.abs(bl - ref).max() <= 1e-3 * max(1.0, np.abs(ref).max()) * 1e-2
+
+
+def test_registration_matches_oracle_trajectory():
+    ds, pert, ((g, feg), (o, feo)) = _setup(seed=9)
+    g.setRegSchedule(2, 2, 5)
+    o.setRegSchedule(2, 2, 5)
+    t0 = feg.pack_transforms(pert)
+    tg = g.registerSlicesToVolume(t0)
+    to = o.registerSlicesToVolume(t0)
+    pg = np.stack([rigid_parameters(m.reshape(4, 4).astype(np.float64)) for m in tg])
+    po = np.stack([rigid_parameters(m.reshape(4, 4).astype(np.float64)) for m in to])
+    d = np.abs(pg - po).max(axis=1)
+    assert np.mean(d <= 1e-3) >= 0.9, d
+    assert d.max() <= 0.5, d
+    assert abs(g.reg_evaluations - o.reg_evaluations) <= 0.1 * o.reg_evaluations
+    # it actually moved the slices, towards higher similarity
+    assert np.abs(tg - t0).max() > 1e-3
+    s0 = g.evaluateCostsMultipleSlices(t0, 0)
+    s1 = g.evaluateCostsMultipleSlices(tg, 0)
+    assert s1[s0 != 0].mean() > s0[s0 != 0].mean()
+
+
+def test_registration_empty_and_errors():
+    import torch
+    from fetalreconstruction_b200.reconstruction import Reconstruction, SVRError
+    g = Reconstruction(0)
+    with pytest.raises(SVRError):
+        g.regS, g.regW, g.regH = 1, 4, 4
+        g.registerSlicesToVolume(np.zeros((1, 16), np.float32))      # no storage yet
+    g.InitReconstructionVolume((8, 8, 8), (1, 1, 1), None)
+    g.initRegStorageVolumes((4, 4, 0), (1, 1, 1))
+    g.FillRegSlices(np.zeros(0, np.float32), None)
+    g.updateResampledSlicesI2W(np.zeros((0, 16), np.float32))
+    g.prepareSliceToVolumeReg()
+    assert g.registerSlicesToVolume(np.zeros((0, 16), np.float32)).shape == (0, 16)
