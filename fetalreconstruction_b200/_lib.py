@@ -11,6 +11,7 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SVR_B200_LIB", os.path.join(HERE, "csrc", "libsvr_b200.so"))
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "svr_abi.h")
+HEADER_PATHS = [HEADER_PATH, os.path.join(os.path.dirname(HERE), "include", "pvr_abi.h")]
 
 _lib = None
 
@@ -74,6 +75,34 @@ _SIGNATURES = {
     "svr_reg_evaluate": (ip, [vp, vp, ip, vp]),
     "svr_reg_evaluations": (C.c_int64, [vp]),
     "svr_reg_debug_get": (ip, [vp, ip, vp]),
+    "pvr_create": (ip, [C.POINTER(vp), ip]),
+    "pvr_recon_init": (ip, [vp, ip, ip, ip, fp, fp, fp, vp, vp]),
+    "pvr_recon_set_mask": (ip, [vp, vp]),
+    "pvr_recon_reset": (ip, [vp]),
+    "pvr_recon_reset_addon_cmap": (ip, [vp]),
+    "pvr_recon_equalize": (ip, [vp]),
+    "pvr_recon_copy_from_host": (ip, [vp, vp]),
+    "pvr_recon_copy_to_host": (ip, [vp, vp]),
+    "pvr_patches_init": (ip, [vp, ip, ip, ip, vp, vp]),
+    "pvr_patches_set_matrices": (ip, [vp, vp, vp, vp, vp]),
+    "pvr_patches_set_spx_masks": (ip, [vp, vp, ip]),
+    "pvr_patches_copy_from_host": (ip, [vp, vp]),
+    "pvr_patches_copy_to_host": (ip, [vp, vp]),
+    "pvr_set_psf": (ip, [vp, vp, vp, fp]),
+    "pvr_init_patch_based_recon": (ip, [vp, ip, vp, ip, ip, ip, vp]),
+    "pvr_psf_reconstruction": (ip, [vp]),
+    "pvr_simulate_patches": (ip, [vp]),
+    "pvr_superresolution_run": (ip, [vp]),
+    "pvr_superresolution_regularize": (ip, [vp, ip, fp, fp, fp, fp, fp]),
+    "pvr_rs_initialize_em_values": (ip, [vp]),
+    "pvr_rs_initialize_robust_statistics": (ip, [vp, F]),
+    "pvr_rs_estep_device": (ip, [vp, fp, fp, fp, vp]),
+    "pvr_rs_get_scales_weights": (ip, [vp, vp, vp]),
+    "pvr_rs_set_scales_weights": (ip, [vp, vp, vp]),
+    "pvr_host_patch_em": (ip, [ip, vp, vp, vp, vp, fp, vp, vp]),
+    "pvr_rs_mstep": (ip, [vp, ip, fp, F, F, F]),
+    "pvr_rs_scale": (ip, [vp, vp]),
+    "pvr_debug_get": (ip, [vp, ip, vp]),
     "svr_host_slice_em": (ip, [ip, vp, vp, vp, vp, ip, vp, ip, dp, vp]),
     "svr_host_small_slices": (ip, [ip, vp, vp, I]),
     "svr_host_partition": (ip, [ip, vp, ip, ip, I, I]),
@@ -82,10 +111,12 @@ _SIGNATURES = {
 
 def declared_symbols() -> list[str]:
     """Every function include/svr_abi.h declares (used by the CPU test that checks the exports)."""
-    with open(HEADER_PATH) as f:
-        text = f.read()
+    text = ""
+    for path in HEADER_PATHS:
+        with open(path) as f:
+            text += f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(svr_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b((?:svr|pvr)_[a-z0-9_]+)\s*\(", text)))
 
 
 def load():

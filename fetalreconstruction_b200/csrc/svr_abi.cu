@@ -108,6 +108,7 @@ int svr_destroy(svr_context* c)
     dev_free(&c->scales_mstep); dev_free(&c->slice_weights); dev_free(&c->slice_tmp); dev_free(&c->geom);
     dev_free(&c->mats); dev_free(&c->dims); dev_free(&c->partials);
     svr_reg_free(c);
+    svr_pvr_free(c);
     prof_fold(c);
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->cub_tmp) cudaFree(c->cub_tmp);

@@ -8,6 +8,24 @@
 #define SVR_PSF_CENTRE 7       // (MAX_PSF_SUPPORT - 1) / 2, reconstruction_cuda2.cu:219
 #define SVR_STEP 0.0001f       // __step, include/reconstruction_cuda2.cuh:54
 
+// Flavour traits: SVR (reconstruction_cuda2.cu) and PVR (patchBased*_gpu.cu, include/reconConfig.cuh:119-140,
+// include/pointSpreadFunction.cuh) run the same tap loop with different constants.
+struct SvrTraits {
+    static constexpr int SUP = 16;      // MAX_PSF_SUPPORT, reconstruction_cuda2.cuh:74 -> offsets -7..+8
+    static constexpr int CEN = 7;
+    // abs(oldPSF - psfval) < PSF_EPSILON with a DOUBLE 1e-5 (cuda2.cu:238): skipped iff the float difference is
+    // <= 1e-5f (the largest float below the double literal)
+    static __device__ __forceinline__ bool accept(float old, float psf) { return !(fabsf(old - psf) <= 1.0e-5f); }
+    static __device__ __forceinline__ bool sume_ok(float s) { return s > 0.5f; }          // cuda2.cu:251
+};
+struct PvrTraits {
+    static constexpr int SUP = 12;      // MAX_PSF_SUPPORT, reconConfig.cuh:140 -> offsets -5..+6
+    static constexpr int CEN = 5;
+    // PSF_EPSILON is a FLOAT literal here (reconConfig.cuh:138)
+    static __device__ __forceinline__ bool accept(float old, float psf) { return !(fabsf(old - psf) < 1.0e-5f); }
+    static __device__ __forceinline__ bool sume_ok(float s) { return s > 1.0e-5f; }       // patchBasedPSFReconstruction_gpu.cu:110
+};
+
 // Per-slice geometry, rebuilt on the device whenever the matrices / voxel sizes change
 // (svr_set_slice_matrices, svr_set_slice_dims).  16-byte aligned.
 //
@@ -89,6 +107,7 @@ __device__ __forceinline__ int f2i_clamped(float f)
     return __float2int_rn(f);
 }
 
+template <class TR>
 __device__ __forceinline__ PixelSetup pixel_setup(const SliceGeom& g, const VolGeom& vg, int x, int y)
 {
     PixelSetup ps;
@@ -102,7 +121,7 @@ __device__ __forceinline__ PixelSetup pixel_setup(const SliceGeom& g, const VolG
     ps.ex = ((q.x - p.x) * g.dimx - vg.psf_c[0]) * g.kx;
     ps.ey = ((q.y - p.y) * g.dimy - vg.psf_c[1]) * g.ky;
     ps.ez = ((q.z - p.z) * g.dimz - vg.psf_c[2]) * g.kz;
-    const int lo = SVR_PSF_CENTRE, hi = SVR_PSF_SUPPORT - 1 - SVR_PSF_CENTRE;
+    const int lo = TR::CEN, hi = TR::SUP - 1 - TR::CEN;
     ps.interior = ps.cx - lo >= 0 && ps.cx + hi < vg.vx && ps.cy - lo >= 0 && ps.cy + hi < vg.vy &&
                   ps.cz - lo >= 0 && ps.cz + hi < vg.vz;
     return ps;
@@ -123,7 +142,7 @@ __device__ __forceinline__ PixelSetup pixel_setup(const SliceGeom& g, const VolG
 // (2 ex2 per segment instead of 1 per tap: the MUFU unit is the busiest pipe of these kernels); the
 // accumulated rounding (<= ~2.5e-6 relative after 7 steps) is of the size of the ex2.approx argument
 // rounding of the direct form.  Slices with extreme through-plane scaling use the direct form.
-template <bool INTERIOR, bool RECUR, class Tap, class RowEnd>
+template <class TR, bool INTERIOR, bool RECUR, class Tap, class RowEnd>
 __device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, Tap&& tap,
                                          RowEnd&& row_end)
 {
@@ -132,26 +151,26 @@ __device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, 
     const float bx1 = g.bx[1], by1 = g.by[1], bz1 = g.bz[1];
     const float bx2 = g.bx[2], by2 = g.by[2], bz2 = g.bz[2];
     const float two_b = g.two_b, bb = g.bb, kappa = g.kappa;
-    constexpr int HALF = SVR_PSF_SUPPORT / 2;
+    constexpr int HALF = TR::SUP / 2;
 #pragma unroll 1
-    for (int oz = -SVR_PSF_CENTRE; oz <= SVR_PSF_SUPPORT - 1 - SVR_PSF_CENTRE; ++oz) {
+    for (int oz = -TR::CEN; oz <= TR::SUP - 1 - TR::CEN; ++oz) {
         const int zi = INTERIOR ? ps.cz + oz : max(ps.cz + oz, 0);
         if (!INTERIOR && zi >= vz) continue;
         const float foz = (float)oz;
         const float zx = fmaf(foz, bx2, ps.ex), zy = fmaf(foz, by2, ps.ey), zz = fmaf(foz, bz2, ps.ez);
 #pragma unroll 1
-        for (int oy = -SVR_PSF_CENTRE; oy <= SVR_PSF_SUPPORT - 1 - SVR_PSF_CENTRE; ++oy) {
+        for (int oy = -TR::CEN; oy <= TR::SUP - 1 - TR::CEN; ++oy) {
             const int yi = INTERIOR ? ps.cy + oy : max(ps.cy + oy, 0);
             if (!INTERIOR && yi >= vy) continue;
             const float foy = (float)oy;
             const float rx = fmaf(foy, bx1, zx), ry = fmaf(foy, by1, zy), rz = fmaf(foy, bz1, zz);
             const int rowbase = (zi * vy + yi) * vx;
-            const int v0 = rowbase + ps.cx - SVR_PSF_CENTRE;
+            const int v0 = rowbase + ps.cx - TR::CEN;
             float old = FLT_MAX;
             float gz = 0.f, rho = 0.f;
 #pragma unroll
-            for (int i = 0; i < SVR_PSF_SUPPORT; ++i) {
-                const float fox = (float)(i - SVR_PSF_CENTRE);
+            for (int i = 0; i < TR::SUP; ++i) {
+                const float fox = (float)(i - TR::CEN);
                 float gauss;
                 if (RECUR) {
                     if (i % HALF == 0) {                  // (re)start a segment with direct evaluations
@@ -166,14 +185,12 @@ __device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, 
                     gauss = ex2_approx(-(dz * dz));
                 }
                 const float psf = sinc2_eval(fmaf(fox, bx0, rx), fmaf(fox, by0, ry)) * gauss;
-                // abs(oldPSF - psfval) < PSF_EPSILON with a double 1e-5 (cuda2.cu:238): true iff the float
-                // difference is <= 1e-5f (the largest float below the double literal).
-                const bool accept = !(fabsf(old - psf) <= 1.0e-5f);
+                const bool accept = TR::accept(old, psf);
                 old = accept ? psf : old;
                 if (INTERIOR) {
                     tap(i, accept ? psf : 0.0f, accept, v0 + i);
                 } else {
-                    const int xi = max(ps.cx + i - SVR_PSF_CENTRE, 0);
+                    const int xi = max(ps.cx + i - TR::CEN, 0);
                     const bool ok = accept && xi < vx;
                     tap(i, ok ? psf : 0.0f, ok, rowbase + xi);
                 }
@@ -184,16 +201,16 @@ __device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, 
 }
 
 // Dispatch on the (per-thread) interior flag and the (per-slice) recurrence flag.
-template <class Tap, class RowEnd>
+template <class TR, class Tap, class RowEnd>
 __device__ __forceinline__ void psf_rows_dispatch(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, Tap&& tap,
                                                   RowEnd&& row_end)
 {
     if (g.recur) {
-        if (ps.interior) psf_rows<true, true>(g, vg, ps, tap, row_end);
-        else psf_rows<false, true>(g, vg, ps, tap, row_end);
+        if (ps.interior) psf_rows<TR, true, true>(g, vg, ps, tap, row_end);
+        else psf_rows<TR, false, true>(g, vg, ps, tap, row_end);
     } else {
-        if (ps.interior) psf_rows<true, false>(g, vg, ps, tap, row_end);
-        else psf_rows<false, false>(g, vg, ps, tap, row_end);
+        if (ps.interior) psf_rows<TR, true, false>(g, vg, ps, tap, row_end);
+        else psf_rows<TR, false, false>(g, vg, ps, tap, row_end);
     }
 }
 

@@ -72,10 +72,14 @@ struct svr_context {
     float recon_i2w[16]{}, recon_w2i[16]{};
     float quality_factor = 1.0f;
     int sm_count = 148;
+    int flavor = 0;                // 0 = SVR constants, 1 = PVR constants (svr_common.cuh traits)
+    char* spx = nullptr;           // PVR superpixel masks, char[S][64*64] ('1' = inside)
+    int use_spx = 0;
     void* reg = nullptr;           // RegState (svr_reg.cu), owned
     void* pvr = nullptr;           // PvrState (pvr.cu), owned
 };
 void svr_reg_free(svr_context* c);
+void svr_pvr_free(svr_context* c);
 
 // error helper used by every translation unit
 int svr_fail(svr_context* ctx, const char* what, cudaError_t e, const char* file, int line);
@@ -116,5 +120,7 @@ int svr_launch_scale_volume_sums(svr_context* c, double out2[2]);
 int svr_launch_scale_volume_apply(svr_context* c, float scale);
 int svr_launch_restore(svr_context* c, const float* d_factors, const int* d_index);
 int svr_launch_compact_valid(svr_context* c);
+int svr_launch_unpack_acc(svr_context* c);
+int svr_launch_equalize_inplace(svr_context* c);
 int svr_launch_deinterleave(svr_context* c, const float2* src, float* dst, int component);
 int svr_launch_flags_to_int(svr_context* c, const unsigned char* src, int* dst, size_t n);

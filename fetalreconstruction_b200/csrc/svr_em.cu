@@ -12,42 +12,59 @@
 #define EM_THREADS 256
 
 // ---- K12: InitializeEMValuesKernel (reconstruction_cuda2.cu:3241-3267) ------------------------
-__global__ void init_em_kernel(size_t n, const float* __restrict__ slices, float* __restrict__ weights)
+// PVR (patchBasedRobustStatistics_gpu.cu:57-78) also zeroes the weight of pixels that are exactly 0.
+__global__ void init_em_kernel(size_t n, const float* __restrict__ slices, float* __restrict__ weights, int flavor)
 {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        weights[i] = (slices[i] != -1.0f) ? 1.0f : 0.0f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float s = slices[i];
+        weights[i] = (s != -1.0f && (flavor == 0 || s != 0.0f)) ? 1.0f : 0.0f;
+    }
 }
 int svr_launch_init_em(svr_context* c)
 {
-    init_em_kernel<<<c->sm_count * 8, EM_THREADS, 0, c->stream>>>(c->NP, c->slices, c->weights);
+    init_em_kernel<<<c->sm_count * 8, EM_THREADS, 0, c->stream>>>(c->NP, c->slices, c->weights, c->flavor);
     SVR_KERNEL_CHECK(c);
     return 0;
 }
 
 // G_ / M_ (reconstruction_cuda2.cu:62-70)
-__device__ __forceinline__ float G_(float x, float s) { return SVR_STEP * __expf(-x * x / (2.0f * s)) / (sqrtf(6.28f * s)); }
-__device__ __forceinline__ float M_(float m) { return m * SVR_STEP; }
+// (PVR: __step = 1e-5, include/reconConfig.cuh:120)
+__device__ __forceinline__ float G_(float x, float s, float step) { return step * __expf(-x * x / (2.0f * s)) / (sqrtf(6.28f * s)); }
+__device__ __forceinline__ float M_(float m, float step) { return m * step; }
 
 // ---- K7 + K8 fused: EStepKernel3D_tex + slice potentials (cuda2.cu:2766-2813, 2816-2911) ------
 // grid = (chunks, S).  slice_acc[2k] += sum (1-w)^2, slice_acc[2k+1] += n over pixels with simweight > 0.99.
 __global__ void __launch_bounds__(EM_THREADS)
 estep_kernel(int P, const float* __restrict__ slices, const float* __restrict__ simslices,
              const float* __restrict__ simweights, const float* __restrict__ scales, float m_, float sigma_, float mix_,
-             float* __restrict__ weights, double* __restrict__ slice_acc)
+             float* __restrict__ weights, double* __restrict__ slice_acc, int flavor)
 {
     const int k = blockIdx.y;
     const size_t base = (size_t)k * P;
     const float scale = scales[k];
-    const float m = M_(m_);
+    const float step = flavor == 0 ? SVR_STEP : 0.00001f;
+    const float m = M_(m_, step);
     float sum = 0.f, num = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
         const float s = slices[base + i];
         const float sw = simweights[base + i];
-        float w = 0.0f;                                   // cudaMemsetAsync(weights, 0) at cuda2.cu:2881
-        if (!((s == -1.0f) || sw <= 0.0f)) {
-            const float e = s * scale - simslices[base + i];
-            const float g = G_(e, sigma_);
-            w = (g * mix_) / (g * mix_ + m * (1.0f - mix_));
+        float w;
+        if (flavor == 0) {
+            w = 0.0f;                                     // cudaMemsetAsync(weights, 0) at cuda2.cu:2881
+            if (!((s == -1.0f) || sw <= 0.0f)) {
+                const float e = s * scale - simslices[base + i];
+                const float g = G_(e, sigma_, step);
+                w = (g * mix_) / (g * mix_ + m * (1.0f - mix_));
+            }
+        } else {
+            // PVR EStepKernel gates on the PREVIOUS weight and leaves gated pixels untouched
+            // (patchBasedRobustStatistics_gpu.cu:121-124)
+            w = weights[base + i];
+            if (!((s == -1.0f) || w <= 0.0f)) {
+                const float e = s * scale - simslices[base + i];
+                const float g = G_(e, sigma_, step);
+                w = (float)((double)(g * mix_) / ((double)(g * mix_) + (double)m * (1.0 - (double)mix_)));
+            }
         }
         weights[base + i] = w;
         if ((double)sw > 0.99) {                          // transformSlicePotential compares against a double literal
@@ -90,7 +107,7 @@ int svr_launch_estep(svr_context* c, float m, float sigma, float mix)
     double* acc = c->partials;                            // [2*S] doubles, zeroed
     SVR_CUDA(c, cudaMemsetAsync(acc, 0, sizeof(double) * 2 * c->S, c->stream));
     estep_kernel<<<slice_grid(c), EM_THREADS, 0, c->stream>>>(c->Nx * c->Ny, c->slices, c->simslices, c->simweights,
-                                                              c->scales, m, sigma, mix, c->weights, acc);
+                                                              c->scales, m, sigma, mix, c->weights, acc, c->flavor);
     SVR_KERNEL_CHECK(c);
     potential_finish_kernel<<<divup_i(c->S, 128), 128, 0, c->stream>>>(c->S, acc, c->slice_tmp);
     SVR_KERNEL_CHECK(c);
@@ -346,7 +363,7 @@ __constant__ int c_dirs[13][3] = {
 
 __global__ void reg_prep_kernel(size_t V, const float* __restrict__ recon, float2* __restrict__ acc2,
                                 const unsigned char* __restrict__ mask, float* __restrict__ post, int adaptive,
-                                float alpha, float min_i, float max_i)
+                                float alpha, float min_i, float max_i, int flavor)
 {
     for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < V; v += (size_t)gridDim.x * blockDim.x) {
         float2 a = acc2[v];
@@ -354,8 +371,13 @@ __global__ void reg_prep_kernel(size_t V, const float* __restrict__ recon, float
         if (!adaptive && a.y != 0.f) { a.x = a.x / a.y; a.y = 1.0f; }
         acc2[v] = a;
         float r = recon[v] + a.x * alpha;
-        if ((double)r < (double)min_i * 0.9) r = (float)((double)min_i * 0.9);
-        if ((double)r > (double)max_i * 1.1) r = (float)((double)max_i * 1.1);
+        if (flavor == 0) {     // double literals in cuda2.cu:1962-1965, float literals in patchBasedSuperresolution_gpu.cu:176-179
+            if ((double)r < (double)min_i * 0.9) r = (float)((double)min_i * 0.9);
+            if ((double)r > (double)max_i * 1.1) r = (float)((double)max_i * 1.1);
+        } else {
+            if (r < min_i * 0.9f) r = min_i * 0.9f;
+            if (r > max_i * 1.1f) r = max_i * 1.1f;
+        }
         post[v] = r;
     }
 }
@@ -417,7 +439,7 @@ reg_kernel(int vx, int vy, int vz, const float* __restrict__ original, const flo
 int svr_launch_regularize(svr_context* c, int adaptive, float alpha, float min_i, float max_i, float delta, float lambda)
 {
     ProfScope prof(c, 3);
-    reg_prep_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->recon, c->acc2, c->mask_u8, c->recon_tmp1, adaptive, alpha, min_i, max_i);
+    reg_prep_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->recon, c->acc2, c->mask_u8, c->recon_tmp1, adaptive, alpha, min_i, max_i, c->flavor);
     SVR_KERNEL_CHECK(c);
     dim3 block(64, 4, 1), grid(divup_i(c->vx, 64), divup_i(c->vy, 4), c->vz);
     reg_kernel<<<grid, block, 0, c->stream>>>(c->vx, c->vy, c->vz, c->recon, c->recon_tmp1, c->acc2, c->recon_tmp2, delta, alpha, lambda);

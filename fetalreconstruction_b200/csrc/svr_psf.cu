@@ -38,18 +38,26 @@ struct Mat16 { float m[16]; };
 
 __global__ void build_geom_kernel(int S, const float* __restrict__ T, const float* __restrict__ Tinv,
                                   const float* __restrict__ I2W, const float* __restrict__ W2I,
-                                  const float* __restrict__ dims, Mat16 reconI2W, SliceGeom* __restrict__ out)
+                                  const float* __restrict__ dims, Mat16 reconI2W, SliceGeom* __restrict__ out, int flavor)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= S) return;
     float t1[16], comb[16];
-    mat44_mul(W2I + 16 * k, Tinv + 16 * k, t1);
-    mat44_mul(t1, reconI2W.m, comb);
+    if (flavor == 0) {          // SVR: (W2I * Tinv) * reconI2W, cuda2.cu:223
+        mat44_mul(W2I + 16 * k, Tinv + 16 * k, t1);
+        mat44_mul(t1, reconI2W.m, comb);
+    } else {                    // PVR: W2I * (InvTransformation * reconstructedI2W), patchBasedPSFReconstruction_gpu.cu:78
+        mat44_mul(Tinv + 16 * k, reconI2W.m, t1);
+        mat44_mul(W2I + 16 * k, t1, comb);
+    }
     SliceGeom g;
     for (int i = 0; i < 12; ++i) { g.i2w[i] = I2W[16 * k + i]; g.t[i] = T[16 * k + i]; g.a[i] = comb[i]; }
-    const float dx = dims[3 * k + 0], dy = dims[3 * k + 1], dz = dims[3 * k + 2];
+    const float dx = dims[3 * k + 0], dy = dims[3 * k + 1];
+    // PVR: sigma_z = dim.z and the through-plane offset is additionally divided by 2.5
+    // (pointSpreadFunction.cuh:76,112); SVR: sigma_z = dim.z / 2.3548 (cuda2.cu:114)
+    const float sigmaz = flavor == 0 ? dims[3 * k + 2] / 2.3548f : dims[3 * k + 2];
+    const float dz = flavor == 0 ? dims[3 * k + 2] : dims[3 * k + 2] / 2.5f;
     g.dimx = dx; g.dimy = dy; g.dimz = dz;
-    const float sigmaz = dz / 2.3548f;
     g.kx = dx / 2.3548f * 3.14159265359f;           // sPos.x * dim.x / 2.3548, then R = pi * x (cuda2.cu:125-128)
     g.ky = dy / 2.3548f * 3.14159265359f;
     g.kz = 0.84932180028801907f / sigmaz;           // sqrt(log2(e) / 2) / sigma_z: exp(-z^2/(2 s^2)) = 2^(-(kz z)^2)
@@ -72,7 +80,7 @@ int svr_launch_build_geom(svr_context* c)
     for (int i = 0; i < 16; ++i) ri2w.m[i] = c->recon_i2w[i];
     const size_t n = (size_t)c->S * 16;
     build_geom_kernel<<<divup_i(c->S, 128), 128, 0, c->stream>>>(c->S, c->mats, c->mats + n, c->mats + 2 * n, c->mats + 3 * n,
-                                                                 c->dims, ri2w, c->geom);
+                                                                 c->dims, ri2w, c->geom, c->flavor);
     SVR_KERNEL_CHECK(c);
     return 0;
 }
@@ -81,19 +89,19 @@ int svr_launch_build_geom(svr_context* c)
 // Flush one interior x-row of contributions p[0..15] (voxels v0 .. v0+15) scaled by (a, c) as paired
 // 128-bit reductions.  The pairs must be 16-byte aligned, so an odd v0 shifts the row by one voxel
 // (17 selects); the accumulator is allocated with 2 voxels of slack for the zero half of the last pair.
-__device__ __forceinline__ void red_row_paired(float2* __restrict__ acc2, int v0, const float (&p)[SVR_PSF_SUPPORT],
-                                               float a, float c)
+template <int SUP>
+__device__ __forceinline__ void red_row_paired(float2* __restrict__ acc2, int v0, const float (&p)[SUP], float a, float c)
 {
     const bool odd = (v0 & 1) != 0;
     float4* base = reinterpret_cast<float4*>(acc2 + (v0 - (odd ? 1 : 0)));
-    float q[SVR_PSF_SUPPORT + 2];
+    float q[SUP + 2];
     q[0] = odd ? 0.0f : p[0];
 #pragma unroll
-    for (int j = 1; j < SVR_PSF_SUPPORT; ++j) q[j] = odd ? p[j - 1] : p[j];
-    q[SVR_PSF_SUPPORT] = odd ? p[SVR_PSF_SUPPORT - 1] : 0.0f;
-    q[SVR_PSF_SUPPORT + 1] = 0.0f;
+    for (int j = 1; j < SUP; ++j) q[j] = odd ? p[j - 1] : p[j];
+    q[SUP] = odd ? p[SUP - 1] : 0.0f;
+    q[SUP + 1] = 0.0f;
 #pragma unroll
-    for (int m = 0; m < SVR_PSF_SUPPORT / 2 + 1; ++m) {
+    for (int m = 0; m < SUP / 2 + 1; ++m) {
         const float u = q[2 * m], w = q[2 * m + 1];
         if (u + w > 0.0f)                                  // psf >= 0: skip all-zero pairs (and NaNs)
             atomicAdd(base + m, make_float4(u * a, u * c, w * a, w * c));
@@ -104,12 +112,13 @@ __device__ __forceinline__ void red_row_paired(float2* __restrict__ acc2, int v0
 // K1: gaussianReconstructionKernel3D_tex (reconstruction_cuda2.cu:176-295).
 // Pass 1: sume = sum of accepted in-volume taps (mask ignored, quirk Q3); stored only if > 0.5.
 // Pass 2: scatter psf/sume * {s*scale, 1}; flag the pixel if any accepted tap landed on a masked voxel.
+template <class TR>
 __global__ void __launch_bounds__(128, SVR_MINB)
 gaussian_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
                         const float* __restrict__ slices, const float* __restrict__ scales,
                         const SliceGeom* __restrict__ geom, VolGeom vg, const unsigned char* __restrict__ mask,
                         float2* __restrict__ acc2, float* __restrict__ psf_sums, unsigned char* __restrict__ voxel_flag,
-                        int* __restrict__ slice_count)
+                        int* __restrict__ slice_count, const char* __restrict__ spx)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_valid) return;
@@ -118,24 +127,27 @@ gaussian_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx
     const int y = pix / Nx, x = pix - y * Nx;
     const SliceGeom& g = geom[k];
     const float s = slices[idx] * scales[k];
-    const PixelSetup ps = pixel_setup(g, vg, x, y);
+    // PVR superpixels: sume only accumulates when the pixel's own flag is '1' (patchBasedPSFReconstruction_gpu.cu:99),
+    // i.e. other pixels end with sume = 0 and return; the mask is char[64*64] per patch, indexed x + 64*y.
+    if (spx && spx[(size_t)k * 4096 + x + 64 * y] != '1') return;
+    const PixelSetup ps = pixel_setup<TR>(g, vg, x, y);
 
     float sume = 0.f;
-    psf_rows_dispatch(g, vg, ps, [&](int, float psf, bool, int) { sume += psf; }, [](int) {});
-    if (!(sume > 0.5f)) return;
+    psf_rows_dispatch<TR>(g, vg, ps, [&](int, float psf, bool, int) { sume += psf; }, [](int) {});
+    if (!TR::sume_ok(sume)) return;
     psf_sums[idx] = sume;
 
     const float inv = 1.0f / sume;
     const float sv = s * inv;
     bool any = false;
     if (ps.interior) {
-        float p[SVR_PSF_SUPPORT];
+        float p[TR::SUP];
         auto tap = [&](int i, float psf, bool ok, int v) { p[i] = psf; if (ok && mask[v]) any = true; };
-        auto row = [&](int v0) { red_row_paired(acc2, v0, p, sv, inv); };
-        if (g.recur) psf_rows<true, true>(g, vg, ps, tap, row);
-        else psf_rows<true, false>(g, vg, ps, tap, row);
+        auto row = [&](int v0) { red_row_paired<TR::SUP>(acc2, v0, p, sv, inv); };
+        if (g.recur) psf_rows<TR, true, true>(g, vg, ps, tap, row);
+        else psf_rows<TR, true, false>(g, vg, ps, tap, row);
     } else {
-        psf_rows_dispatch(g, vg, ps,
+        psf_rows_dispatch<TR>(g, vg, ps,
             [&](int, float psf, bool ok, int v) {
                 if (ok) {
                     atomicAdd(&acc2[v], make_float2(psf * sv, psf * inv));
@@ -154,9 +166,14 @@ int svr_launch_gaussian_scatter(svr_context* c)
 {
     if (c->n_valid == 0) return 0;
     ProfScope prof(c, 0);
-    gaussian_scatter_kernel<<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
-        c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2,
-        c->psf_sums, c->voxel_flag, c->slice_count);
+    if (c->flavor == 0)
+        gaussian_scatter_kernel<SvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
+            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2,
+            c->psf_sums, c->voxel_flag, c->slice_count, nullptr);
+    else
+        gaussian_scatter_kernel<PvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
+            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2,
+            c->psf_sums, c->voxel_flag, c->slice_count, c->use_spx ? c->spx : nullptr);
     SVR_KERNEL_CHECK(c);
     return 0;
 }
@@ -164,6 +181,7 @@ int svr_launch_gaussian_scatter(svr_context* c)
 // ---------------------------------------------------------------------------------------------
 // K2: simulateSlicesKernel3D_tex (reconstruction_cuda2.cu:298-404).
 // pack2[v] = {recon[v]*m, m} with m = (mask != 0), so a tap is one predicated 64-bit load + 2 FFMA.
+template <class TR>
 __global__ void __launch_bounds__(128, SVR_MINB)
 simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
                 const SliceGeom* __restrict__ geom, VolGeom vg, const float2* __restrict__ pack2,
@@ -178,7 +196,7 @@ simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx
     const int k = idx / P, pix = idx - k * P;
     const int y = pix / Nx, x = pix - y * Nx;
     const SliceGeom& g = geom[k];
-    const PixelSetup ps = pixel_setup(g, vg, x, y);
+    const PixelSetup ps = pixel_setup<TR>(g, vg, x, y);
 
     float sim = 0.f, wsum = 0.f;
     auto tap = [&](int, float psf, bool ok, int v) {
@@ -188,7 +206,7 @@ simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx
             wsum = fmaf(psf, pm.y, wsum);
         }
     };
-    psf_rows_dispatch(g, vg, ps, tap, [](int) {});
+    psf_rows_dispatch<TR>(g, vg, ps, tap, [](int) {});
     const float weight = wsum / sume;
     if (weight > 0.f) {
         simslices[idx] = sim / wsum;              // (sum psf/sume * x) / (sum psf/sume)
@@ -202,15 +220,21 @@ int svr_launch_simulate(svr_context* c)
 {
     if (c->n_valid == 0) return 0;
     ProfScope prof(c, 1);
-    simulate_kernel<<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->geom,
-                                                                     c->vg, c->pack2, c->psf_sums, c->simslices,
-                                                                     c->simweights, c->siminside, c->slice_inside);
+    if (c->flavor == 0)
+        simulate_kernel<SvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
+            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->geom, c->vg, c->pack2, c->psf_sums, c->simslices, c->simweights,
+            c->siminside, c->slice_inside);
+    else
+        simulate_kernel<PvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
+            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->geom, c->vg, c->pack2, c->psf_sums, c->simslices, c->simweights,
+            c->siminside, c->slice_inside);
     SVR_KERNEL_CHECK(c);
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3: SuperresolutionKernel3D_tex (reconstruction_cuda2.cu:408-522).
+template <class TR>
 __global__ void __launch_bounds__(128, SVR_MINB)
 superres_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
                         const float* __restrict__ slices, const float* __restrict__ weights,
@@ -235,15 +259,15 @@ superres_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx
     const float aw = cw * sliceVal;
     // A pixel with zero weight adds exact zeros everywhere: skip its 4096 taps.
     if (cw == 0.0f) return;
-    const PixelSetup ps = pixel_setup(g, vg, x, y);
+    const PixelSetup ps = pixel_setup<TR>(g, vg, x, y);
     if (ps.interior) {
-        float p[SVR_PSF_SUPPORT];
+        float p[TR::SUP];
         auto tap = [&](int i, float psf, bool, int) { p[i] = psf; };
-        auto row = [&](int v0) { red_row_paired(acc2, v0, p, aw, cw); };
-        if (g.recur) psf_rows<true, true>(g, vg, ps, tap, row);
-        else psf_rows<true, false>(g, vg, ps, tap, row);
+        auto row = [&](int v0) { red_row_paired<TR::SUP>(acc2, v0, p, aw, cw); };
+        if (g.recur) psf_rows<TR, true, true>(g, vg, ps, tap, row);
+        else psf_rows<TR, true, false>(g, vg, ps, tap, row);
     } else {
-        psf_rows_dispatch(g, vg, ps,
+        psf_rows_dispatch<TR>(g, vg, ps,
             [&](int, float psf, bool ok, int v) { if (ok) atomicAdd(&acc2[v], make_float2(psf * aw, psf * cw)); },
             [](int) {});
     }
@@ -253,9 +277,14 @@ int svr_launch_superres_scatter(svr_context* c)
 {
     if (c->n_valid == 0) return 0;
     ProfScope prof(c, 2);
-    superres_scatter_kernel<<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
-        c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
-        c->geom, c->vg, c->psf_sums, c->acc2);
+    if (c->flavor == 0)
+        superres_scatter_kernel<SvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
+            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
+            c->geom, c->vg, c->psf_sums, c->acc2);
+    else
+        superres_scatter_kernel<PvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
+            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
+            c->geom, c->vg, c->psf_sums, c->acc2);
     SVR_KERNEL_CHECK(c);
     return 0;
 }
@@ -271,8 +300,35 @@ __global__ void pack_volume_kernel(size_t V, const float* __restrict__ recon, co
     }
 }
 
+// PVR reads the volume through a linear-filtered, border-mode 3D texture at UN-OFFSET normalised coordinates
+// (reconVolume.cu:169-187, patchBasedSimulatePatches_gpu.cu:106): texel coordinate pos - 0.5, i.e. the mean of the
+// 8 voxels pos + {-1,0}^3 with out-of-volume voxels reading 0.  The averaged volume is formed once per call here
+// (the reference copies the whole volume into a cudaArray per call instead, patchBasedSimulatePatches_gpu.cu:135).
+__global__ void pack_volume_tex_kernel(int vx, int vy, int vz, const float* __restrict__ recon,
+                                       const unsigned char* __restrict__ mask, float2* __restrict__ pack2)
+{
+    const size_t V = (size_t)vx * vy * vz;
+    for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < V; v += (size_t)gridDim.x * blockDim.x) {
+        if (!mask[v]) { pack2[v] = make_float2(0.f, 0.f); continue; }
+        const int x = (int)(v % vx), y = (int)((v / vx) % vy), z = (int)(v / ((size_t)vx * vy));
+        float s = 0.f;
+        for (int dz = -1; dz <= 0; ++dz)
+            for (int dy = -1; dy <= 0; ++dy)
+                for (int dx = -1; dx <= 0; ++dx) {
+                    const int xx = x + dx, yy = y + dy, zz = z + dz;
+                    if (xx >= 0 && yy >= 0 && zz >= 0) s += 0.125f * recon[xx + (size_t)yy * vx + (size_t)zz * vx * vy];
+                }
+        pack2[v] = make_float2(s, 1.0f);
+    }
+}
+
 int svr_launch_pack_volume(svr_context* c)
 {
+    if (c->flavor == 1) {
+        pack_volume_tex_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->vx, c->vy, c->vz, c->recon, c->mask_u8, c->pack2);
+        SVR_KERNEL_CHECK(c);
+        return 0;
+    }
     pack_volume_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->recon, c->mask_u8, c->pack2);
     SVR_KERNEL_CHECK(c);
     return 0;
@@ -306,6 +362,38 @@ __global__ void deinterleave_kernel(size_t V, const float2* __restrict__ src, fl
 int svr_launch_deinterleave(svr_context* c, const float2* src, float* dst, int component)
 {
     deinterleave_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, src, dst, component);
+    SVR_KERNEL_CHECK(c);
+    return 0;
+}
+
+// PVR: P1 accumulates into recon / volWeights across stacks (ReconVolume::reset once per iteration,
+// irtkPatchBasedReconstruction.cpp:492-497) and equalize is a separate call (reconVolume.cu:59-100).
+__global__ void unpack_acc_kernel(size_t V, const float2* __restrict__ acc2, const unsigned char* __restrict__ mask,
+                                  float* __restrict__ recon, float* __restrict__ volw)
+{
+    for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < V; v += (size_t)gridDim.x * blockDim.x) {
+        float2 a = acc2[v];
+        if (!mask[v]) a = make_float2(0.f, 0.f);
+        recon[v] = a.x;
+        volw[v] = a.y;
+    }
+}
+int svr_launch_unpack_acc(svr_context* c)
+{
+    unpack_acc_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->acc2, c->mask_u8, c->recon, c->volw);
+    SVR_KERNEL_CHECK(c);
+    return 0;
+}
+__global__ void equalize_inplace_kernel(size_t V, float* __restrict__ recon, const float* __restrict__ volw)
+{
+    for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < V; v += (size_t)gridDim.x * blockDim.x) {
+        const float a = recon[v], b = volw[v];
+        recon[v] = (b != 0.f) ? a / b : a;
+    }
+}
+int svr_launch_equalize_inplace(svr_context* c)
+{
+    equalize_inplace_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->recon, c->volw);
     SVR_KERNEL_CHECK(c);
     return 0;
 }

@@ -68,6 +68,7 @@ class Dataset:
     max_intensity: float
     slice_attrs: list | None = None    # ImageAttributes of every slice (for the registration front-end)
     true_trans: np.ndarray | None = None   # the motion each slice was acquired with [S,16]
+    stack_attrs: list | None = None    # ImageAttributes of every stack (PVR patch enumeration)
 
     @property
     def S(self) -> int:
@@ -135,6 +136,7 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
     dims = np.empty((S, 3), np.float32)
     stack_index = np.empty(S, np.int32)
     slice_attrs = []
+    stack_attrs = []
     true_trans = np.empty((S, 16), np.float32)
 
     py, px = torch.meshgrid(torch.arange(Ny, device=dev), torch.arange(Nx, device=dev), indexing="ij")
@@ -152,6 +154,7 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
         xa, ya, za = rotation_axes(*ang)
         stack_attr = ImageAttributes(Nx, Ny, cfg.slices_per_stack, cfg.inplane, cfg.inplane, cfg.spacing,
                                      np.zeros(3), xa, ya, za)
+        stack_attrs.append(stack_attr)
         mrng = np.random.default_rng(cfg.seed + 1000 + st)
         for j in range(cfg.slices_per_stack):
             sa = stack_attr.slice_attributes(j, thickness)
@@ -192,4 +195,4 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
     return Dataset(cfg, vol_attr, ri2w.astype(np.float32).ravel(), rw2i.astype(np.float32).ravel(),
                    mask.cpu().numpy(), truth.cpu().numpy(), slices, i2w, w2i, trans, trans_inv, dims,
                    stack_index, psf_centre_offset(cfg.vol_voxel),
-                   float(pos.min()) if pos.size else 0.0, float(pos.max()) if pos.size else 0.0, slice_attrs, true_trans)
+                   float(pos.min()) if pos.size else 0.0, float(pos.max()) if pos.size else 0.0, slice_attrs, true_trans, stack_attrs)

@@ -1,0 +1,307 @@
+"""Host side of the PVR (patch-to-volume) path on top of include/pvr_abi.h.
+
+`PatchReconstruction` is the ctypes binding (method names follow the reference objects they replace:
+ReconVolume<T>, PatchBasedVolume<T>, patchBasedPSFReconstruction_gpu, patchBasedSimulatePatches_gpu,
+patchBasedSuperresolution_gpu<T>, patchBasedRobustStatistics_gpu<T>); `PVRPipeline` restates the loop of
+irtkPatchBasedReconstruction<T>::run() (source/reconstructionGPU2/irtkPatchBasedReconstruction.cpp:445-587) and
+the scalar state of patchBasedRobustStatistics_gpu (patchBasedRobustStatistics_gpu.cu:746-851, 572-640);
+`generate_2d_patches` restates the CPU patch enumeration PatchBasedObject::generate2DPatches
+(include/patchBasedObject.cuh:176-342).  No arithmetic of the kernels lives here; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .geometry import ImageAttributes
+from .reconstruction import SVRError, _f32, _p
+
+
+class PatchReconstruction:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        if self._lib.pvr_create(C.byref(h), int(device)) != 0:
+            raise SVRError(self._lib.svr_last_error(None).decode())
+        self._h = h
+        self.n = self.pbx = self.pby = 0
+        self.vol_shape = (0, 0, 0)
+        self.patches_per_stack = []
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SVRError(self._lib.svr_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.svr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def V(self):
+        return self.vol_shape[0] * self.vol_shape[1] * self.vol_shape[2]
+
+    @property
+    def NP(self):
+        return self.n * self.pbx * self.pby
+
+    @property
+    def launch_count(self):
+        return int(self._lib.svr_launch_count(self._h))
+
+    # ReconVolume<T>
+    def recon_init(self, size, dim, recon_w2i, recon_i2w):
+        sx, sy, sz = (int(v) for v in size)
+        a, b = _f32(np.asarray(recon_w2i).ravel(), (16,)), _f32(np.asarray(recon_i2w).ravel(), (16,))
+        self._ck(self._lib.pvr_recon_init(self._h, sx, sy, sz, float(dim[0]), float(dim[1]), float(dim[2]), _p(a), _p(b)))
+        self.vol_shape = (sx, sy, sz)
+
+    def recon_setMask(self, mask):
+        m = np.ascontiguousarray(np.asarray(mask).ravel(), np.int8)
+        assert m.size == self.V
+        self._ck(self._lib.pvr_recon_set_mask(self._h, _p(m)))
+
+    def recon_reset(self): self._ck(self._lib.pvr_recon_reset(self._h))
+    def recon_resetAddonCmap(self): self._ck(self._lib.pvr_recon_reset_addon_cmap(self._h))
+    def recon_equalize(self): self._ck(self._lib.pvr_recon_equalize(self._h))
+
+    def recon_copyFromHost(self, data):
+        d = _f32(np.asarray(data).ravel(), (self.V,))
+        self._ck(self._lib.pvr_recon_copy_from_host(self._h, _p(d)))
+
+    def recon_copyToHost(self):
+        out = np.empty(self.V, np.float32)
+        self._ck(self._lib.pvr_recon_copy_to_host(self._h, _p(out)))
+        return out
+
+    # PatchBasedVolume<T>
+    def patches_init(self, pbx, pby, patches_per_stack, stack_dims):
+        pps = np.ascontiguousarray(patches_per_stack, np.int32)
+        sd = _f32(stack_dims, (pps.size, 3))
+        self._ck(self._lib.pvr_patches_init(self._h, int(pbx), int(pby), int(pps.size), _p(pps), _p(sd)))
+        self.pbx, self.pby, self.n = int(pbx), int(pby), int(pps.sum())
+        self.patches_per_stack = [int(v) for v in pps]
+
+    def patches_set_matrices(self, i2w, w2i, transformation, inv_transformation):
+        a, b = _f32(i2w, (self.n, 16)), _f32(w2i, (self.n, 16))
+        t, ti = _f32(transformation, (self.n, 16)), _f32(inv_transformation, (self.n, 16))
+        self._ck(self._lib.pvr_patches_set_matrices(self._h, _p(a), _p(b), _p(t), _p(ti)))
+
+    def patches_set_spx(self, masks, use_spx=True):
+        m = None if masks is None else np.ascontiguousarray(masks, "S1").reshape(self.n, 4096)
+        self._ck(self._lib.pvr_patches_set_spx_masks(self._h, _p(m), int(bool(use_spx))))
+
+    def patches_copyFromHost(self, cube):
+        c = _f32(np.asarray(cube).ravel(), (self.NP,))
+        self._ck(self._lib.pvr_patches_copy_from_host(self._h, _p(c)))
+
+    def patches_copyToHost(self):
+        out = np.empty(max(self.NP, 1), np.float32)
+        self._ck(self._lib.pvr_patches_copy_to_host(self._h, _p(out)))
+        return out[:self.NP].reshape(self.n, self.pby, self.pbx)
+
+    def set_psf(self, psf_size, psf_i2w, quality_factor=1.0):
+        sz = np.ascontiguousarray(psf_size, np.int32)
+        m = _f32(np.asarray(psf_i2w).ravel(), (16,))
+        self._ck(self._lib.pvr_set_psf(self._h, _p(sz), _p(m), float(quality_factor)))
+
+    def initPatchBasedRecon_gpu(self, stack, stack_data, stack_w2i):
+        sz, sy, sx = stack_data.shape
+        d = _f32(np.asarray(stack_data).ravel())
+        m = _f32(np.asarray(stack_w2i).ravel(), (16,))
+        self._ck(self._lib.pvr_init_patch_based_recon(self._h, int(stack), _p(d), sx, sy, sz, _p(m)))
+
+    # hot path
+    def patchBasedPSFReconstruction_gpu(self): self._ck(self._lib.pvr_psf_reconstruction(self._h))
+    def patchBasedSimulatePatches_gpu(self): self._ck(self._lib.pvr_simulate_patches(self._h))
+    def superresolution_run(self): self._ck(self._lib.pvr_superresolution_run(self._h))
+
+    def superresolution_regularize(self, adaptive, alpha, min_intensity, max_intensity, delta, lambda_):
+        self._ck(self._lib.pvr_superresolution_regularize(self._h, int(bool(adaptive)), float(alpha), float(min_intensity),
+                                                          float(max_intensity), float(delta), float(lambda_)))
+
+    # robust statistics
+    def rs_initializeEMValues(self): self._ck(self._lib.pvr_rs_initialize_em_values(self._h))
+
+    def rs_InitializeRobustStatistics(self):
+        s = C.c_float()
+        self._ck(self._lib.pvr_rs_initialize_robust_statistics(self._h, C.byref(s)))
+        return s.value
+
+    def rs_estep_device(self, m, sigma, mix):
+        pot = np.zeros(max(self.n, 1), np.float32)
+        self._ck(self._lib.pvr_rs_estep_device(self._h, float(m), float(sigma), float(mix), _p(pot)))
+        return pot[:self.n]
+
+    def rs_get_scales_weights(self):
+        s, w = np.zeros(max(self.n, 1), np.float32), np.zeros(max(self.n, 1), np.float32)
+        self._ck(self._lib.pvr_rs_get_scales_weights(self._h, _p(s), _p(w)))
+        return s[:self.n], w[:self.n]
+
+    def rs_set_scales_weights(self, scales, weights):
+        s, w = _f32(scales, (self.n,)), _f32(weights, (self.n,))
+        self._ck(self._lib.pvr_rs_set_scales_weights(self._h, _p(s), _p(w)))
+
+    def rs_MStep(self, it, step, sigma, mix, m):
+        s, mi, mm = C.c_float(sigma), C.c_float(mix), C.c_float(m)
+        self._ck(self._lib.pvr_rs_mstep(self._h, int(it), float(step), C.byref(s), C.byref(mi), C.byref(mm)))
+        return s.value, mi.value, mm.value
+
+    def rs_Scale(self):
+        sc = np.zeros(max(self.n, 1), np.float32)
+        self._ck(self._lib.pvr_rs_scale(self._h, _p(sc)))
+        return sc[:self.n]
+
+    def _debug(self, kind, n, dtype):
+        out = np.empty(max(n, 1), dtype)
+        self._ck(self._lib.pvr_debug_get(self._h, kind, _p(out)))
+        return out[:n]
+
+    def debugWeights(self): return self._debug(0, self.NP, np.float32)
+    def debugSimpatches(self): return self._debug(1, self.NP, np.float32)
+    def debugSimweights(self): return self._debug(2, self.NP, np.float32)
+    def debugSiminside(self): return self._debug(3, self.NP, np.int8)
+    def debugConfidenceMap(self): return self._debug(4, self.V, np.float32)
+    def debugAddon(self): return self._debug(5, self.V, np.float32)
+    def debugPSFsums(self): return self._debug(6, self.NP, np.float32)
+
+    def getVolWeights(self):
+        out = np.empty(self.V, np.float32)
+        self._ck(self._lib.svr_get_vol_weights(self._h, _p(out)))
+        return out
+
+
+def host_patch_em(patches_per_stack, patch_potential, scale, patch_weight, step, state5):
+    """EStep host part (patchBasedRobustStatistics_gpu.cu:277-520), literal; returns the potentials the reference used."""
+    lib = _lib.load()
+    pps = np.ascontiguousarray(patches_per_stack, np.int32)
+    pot, sc = _f32(patch_potential), _f32(scale)
+    assert patch_weight.dtype == np.float32 and state5.dtype == np.float32
+    used = np.zeros(max(int(pps.sum()), 1), np.float32)
+    if lib.pvr_host_patch_em(int(pps.size), _p(pps), _p(pot), _p(sc), _p(patch_weight), float(step), _p(state5), _p(used)) != 0:
+        raise SVRError("pvr_host_patch_em: bad argument")
+    return used[:int(pps.sum())]
+
+
+@dataclass
+class PVRParams:
+    """Defaults of patchBasedReconMain.cpp:110-144 / irtkPatchBasedReconstruction.cpp:415, patchBasedSuperresolution_gpu.cu:293-295."""
+    iterations: int = 7            # the loop runs iterations + 1 passes (irtkPatchBasedReconstruction.cpp:445)
+    rec_iterations: int = 7
+    delta: float = 1.0
+    lambda_: float = 0.1
+    adaptive: bool = False
+    step: float = 0.0001           # m_step of patchBasedRobustStatistics_gpu (:877); __step of the kernels is 1e-5
+
+
+class PVRPipeline:
+    """irtkPatchBasedReconstruction<T>::run() from the first iteration on, registration excluded."""
+
+    def __init__(self, backend, min_intensity, max_intensity, params: PVRParams | None = None):
+        self.b = backend
+        self.p = params or PVRParams()
+        self.min_intensity, self.max_intensity = float(min_intensity), float(max_intensity)
+        self.alpha = (0.05 / self.p.lambda_) * self.p.delta * self.p.delta
+        self.sigma = self.mix = self.m = 0.0
+        self.sigma_s, self.mix_s, self.mean_s, self.mean_s2, self.sigma_s2 = 0.025, 0.9, 0.0, 0.0, 0.0
+        self.patch_potential = None
+
+    # patchBasedRobustStatistics_gpu<T>
+    def InitializeRobustStatistics(self):
+        self.sigma = self.b.rs_InitializeRobustStatistics()
+        self.sigma_s, self.mix, self.mix_s = 0.025, 0.9, 0.9
+        self.m = float(np.float32(1.0) / (np.float32(2.1) * np.float32(self.max_intensity)
+                                          - np.float32(1.9) * np.float32(self.min_intensity)))
+
+    def EStep(self):
+        pot = self.b.rs_estep_device(self.m, self.sigma, self.mix)
+        scales, weights = self.b.rs_get_scales_weights()
+        weights = weights.astype(np.float32).copy()
+        state = np.array([self.sigma_s, self.mix_s, self.mean_s, self.mean_s2, self.sigma_s2], np.float32)
+        self.patch_potential = host_patch_em(self.b.patches_per_stack, pot, scales, weights, self.p.step, state)
+        self.sigma_s, self.mix_s, self.mean_s, self.mean_s2, self.sigma_s2 = (float(v) for v in state)
+        self.b.rs_set_scales_weights(scales, weights)
+
+    def MStep(self, it):
+        self.sigma, self.mix, self.m = self.b.rs_MStep(it, self.p.step, self.sigma, self.mix, self.m)
+
+    def Scale(self):
+        return self.b.rs_Scale()
+
+    def iteration(self):
+        b, p = self.b, self.p
+        b.rs_initializeEMValues()
+        b.recon_reset()
+        b.patchBasedPSFReconstruction_gpu()
+        b.recon_equalize()
+        b.patchBasedSimulatePatches_gpu()
+        self.InitializeRobustStatistics()
+        self.EStep()
+        for i in range(p.rec_iterations):
+            self.Scale()
+            b.recon_resetAddonCmap()
+            b.superresolution_run()
+            b.superresolution_regularize(p.adaptive, self.alpha, self.min_intensity, self.max_intensity, p.delta, p.lambda_)
+            b.patchBasedSimulatePatches_gpu()
+            self.MStep(i + 1)
+            self.EStep()
+
+    def run(self, register=None):
+        for it in range(self.p.iterations + 1):
+            if it > 0 and register is not None:
+                register(it)
+            self.iteration()
+        return self.b.recon_copyToHost()
+
+
+def generate_2d_patches(stack: np.ndarray, attr: ImageAttributes, mask: np.ndarray, mask_attr: ImageAttributes,
+                        pbb=(64, 64), stride=(32, 32), thickness=2.5):
+    """PatchBasedObject::generate2DPatches (include/patchBasedObject.cuh:176-342): enumerate pbb-sized boxes on a
+    stride grid over every slice (the grid runs to size + pbb), keep those where more than 1/3 of the pixels are
+    inside the mask and neither 0 nor -1.  Returns (list of patch ImageAttributes, CPU-extracted patch cube)."""
+    pbx, pby = pbb
+    w2i_mask = mask_attr.world_to_image()
+    attrs, cubes = [], []
+    jj, ii = np.meshgrid(np.arange(pby, dtype=np.float64), np.arange(pbx, dtype=np.float64), indexing="ij")
+    for z in range(attr.z):
+        sattr = attr.slice_attributes(z, thickness * 2)
+        s_i2w, s_w2i = sattr.image_to_world(), sattr.world_to_image()
+        sl = stack[z]
+        for y in range(0, attr.y + pby, stride[1]):
+            for x in range(0, attr.x + pbx, stride[0]):
+                pa = ImageAttributes(pbx, pby, 1, attr.dx, attr.dy, thickness * 2, np.zeros(3), sattr.xaxis, sattr.yaxis, sattr.zaxis)
+                p1 = s_i2w @ np.array([x, y, 0, 1.0])
+                p2 = pa.image_to_world() @ np.array([0, 0, 0, 1.0])
+                pa.origin = (p1 - p2)[:3]
+                i2w = pa.image_to_world()
+                m_s = s_w2i @ i2w
+                m_m = w2i_mask @ i2w
+                xs = m_s[0, 0] * ii + m_s[0, 1] * jj + m_s[0, 3]
+                ys = m_s[1, 0] * ii + m_s[1, 1] * jj + m_s[1, 3]
+                xm = m_m[0, 0] * ii + m_m[0, 1] * jj + m_m[0, 3]
+                ym = m_m[1, 0] * ii + m_m[1, 1] * jj + m_m[1, 3]
+                zm = m_m[2, 0] * ii + m_m[2, 1] * jj + m_m[2, 3]
+                ok = (xs >= 0) & (ys >= 0) & (xs < attr.x) & (ys < attr.y)
+                ok &= (xm >= 0) & (ym >= 0) & (zm >= 0) & (xm < mask.shape[2]) & (ym < mask.shape[1]) & (zm < mask.shape[0])
+                # irtkGenericImage::Get(double...) truncates to int
+                xi, yi = np.clip(xs.astype(int), 0, attr.x - 1), np.clip(ys.astype(int), 0, attr.y - 1)
+                mx = np.clip(xm.astype(int), 0, mask.shape[2] - 1)
+                my = np.clip(ym.astype(int), 0, mask.shape[1] - 1)
+                mz = np.clip(zm.astype(int), 0, mask.shape[0] - 1)
+                ok &= mask[mz, my, mx] > 0
+                patch = np.where(ok, sl[yi, xi], 0.0).astype(np.float32)
+                set_count = int(np.count_nonzero(ok & (patch != 0) & (patch != -1)))
+                if set_count > 1.0 / 3.0 * pbx * pby:
+                    attrs.append(pa)
+                    cubes.append(patch)
+    cube = np.stack(cubes) if cubes else np.zeros((0, pby, pbx), np.float32)
+    return attrs, cube
