@@ -80,8 +80,11 @@ def test_psf_reconstruction_simulate_and_em(pair):
     for b in (g, o):
         b.recon_resetAddonCmap()
         b.superresolution_run()
-    check_volume(g.debugAddon(), o.debugAddon(), "addon")
-    check_volume(g.debugConfidenceMap(), o.debugConfidenceMap(), "confidence map")
+    # the CUDA accumulator also holds voxels outside the mask (the per-tap mask test is applied per voxel by the
+    # regulariser prep / equalize): compare inside the mask
+    mk = case["mask"].ravel() > 0
+    check_volume(g.debugAddon()[mk], o.debugAddon()[mk], "addon")
+    check_volume(g.debugConfidenceMap()[mk], o.debugConfidenceMap()[mk], "confidence map")
     for b in (g, o):
         b.superresolution_regularize(False, 0.5, ds.min_intensity, ds.max_intensity, 1.0, 0.1)
     check_volume(g.recon_copyToHost(), o.recon_copyToHost(), "regularised volume")
