@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--workload", default="C3", choices=["C3", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-registration", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -328,6 +329,41 @@ def main():
                    "seconds_per_volume": wall, "finite": bool(np.isfinite(vol).all())}
             vph = 3600.0 / wall
 
+        # ---- slice-to-volume registration (a10): similarity-kernel throughput and one full registration call ----
+        registration = None
+        if not args.no_registration:
+            from fetalreconstruction_b200.registration import RegistrationFrontEnd
+            t0 = time.perf_counter()
+            fe = RegistrationFrontEnd(backend, ds.slices, ds.slice_attrs, cfg.vol_voxel)
+            prep_s = time.perf_counter() - t0
+            backend.updateResampledSlicesI2W(fe.ofs)
+            backend.prepareSliceToVolumeReg()
+            tr = fe.pack_transforms(ds.trans)
+            backend.evaluateCostsMultipleSlices(tr, 0)                 # warm-up
+            backend.profile_reset(); backend.profile_enable(True)
+            n_eval = 5
+            for _ in range(n_eval):
+                backend.evaluateCostsMultipleSlices(tr, 0)
+            backend.profile_enable(False)
+            ev_ms = backend.profile_read()["reg_eval"][0] / n_eval
+            W, H, Sl = backend.regW, backend.regH, backend.regS
+            alg = 3 * 8 * W * H * Sl                                   # 8*W*H per cost evaluation per z-offset (fused)
+            backend.setRegSchedule(2, 4, 20)
+            comm.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            backend.registerSlicesToVolume(tr)
+            torch.cuda.synchronize()
+            reg_s = time.perf_counter() - t0
+            treg = torch.tensor([reg_s], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(treg, op=dist.ReduceOp.MAX)
+            registration = {"kernel": "reg_eval_kernel (fused sample + blur + NCC moments)", "ms_per_cost_evaluation": ev_ms,
+                            "slices": Sl, "slice_size": [W, H], "alg_bytes_per_evaluation": alg,
+                            "alg_GBps": alg / (ev_ms * 1e-3) / 1e9 if ev_ms > 0 else None,
+                            "full_registration_s": float(treg.item()), "cost_evaluations_slice_offsets": backend.reg_evaluations,
+                            "slices_registered_per_s": S_global / float(treg.item()), "host_prep_s": prep_s,
+                            "schedule": "reference default: 2 levels x 4 steps x <=20 iterations, epsilon 1e-4"}
+
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base, _ = run_cpu_baseline(cfg, steps=1, warmup=0)
@@ -337,7 +373,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_json(cfg, world),
                 "volumes_per_hour": vph, "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
-                "gpu_launches": int(ln.item()), "clocks": clocks}
+                "registration": registration, "gpu_launches": int(ln.item()), "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
