@@ -18,17 +18,26 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def svr_case(backend=None):
+# The reference kernels have no x/y bounds check: grid-overhang threads of its (8,8,z) blocks alias
+# into the next row / slice.  Cases that are compared with the REFERENCE's own output therefore use slice sizes
+# that are multiples of 8, where the reference has no overhang threads.
+REF_SVR_SIZE = (24, 24)
+REF_STEPS_SIZE = (40, 32)
+
+
+def svr_case(backend=None, pipeline_cls=None, slice_size=None):
     from fetalreconstruction_b200.phantom import make_dataset, small_config
     from fetalreconstruction_b200.pipeline import SVRPipeline, SVRParams, upload_dataset
     if backend is None:
         from oracle.oracle_backend import OracleReconstruction
         backend = OracleReconstruction()
     cfg = small_config(seed=21, vol=28, n_stacks=2, slices=5, size=24, inplane=1.1, spacing=2.2)
+    if slice_size is not None:          # the reference-generated variant: Nx, Ny multiples of 8 (see REF_SVR_SIZE)
+        cfg.slice_size = tuple(slice_size)
     ds = make_dataset(cfg)
     b = backend
     upload_dataset(b, ds)
-    p = SVRPipeline(b, ds.S, 0, ds.S, params=SVRParams(iterations=1, rec_iterations_last=2))
+    p = (pipeline_cls or SVRPipeline)(b, ds.S, 0, ds.S, params=SVRParams(iterations=1, rec_iterations_last=2))
     p.InitializeEMGPU(ds.slices)
     p.set_schedule(0)
     p.InitializeEMValuesGPU()
