@@ -39,7 +39,10 @@ struct RegState {
     float* resampled = nullptr;   // dev_v_slices_resampled        [S][H][W]
     float* blurred = nullptr;     // dev_v_slices_resampled_float
     float* tmp = nullptr;         // dev_temp_slices (X pass of the per-level blur)
-    float* vol = nullptr;         // snapshot of the volume (the reference's cudaArray copy)
+    float* vol = nullptr;         // unused since the texture path (kept so the free list stays simple)
+    cudaArray_t vol_array = nullptr;      // snapshot of the volume (dev_reconstructed_array, cuda2.cu:3931-3947)
+    cudaTextureObject_t vol_tex = 0;      // linear filter, border addressing, normalised coordinates (cuda2.cu:3950-3956)
+    int ax = 0, ay = 0, az = 0;           // extent of vol_array
     float* ofs = nullptr;         // dev_d_slicesOfs               [S][16]
     float* res_i2w = nullptr;     // dev_d_slicesResampledI2W      [S][16] (kept; unused by the kernels, as in the reference)
     float* M = nullptr;           // dev_recon_matrices            [S][16]
@@ -80,6 +83,8 @@ void svr_reg_free(svr_context* c)
     void* ptrs[] = { r->resampled, r->blurred, r->tmp, r->vol, r->ofs, r->res_i2w, r->M, r->Morig, r->sim, r->grad,
                      r->active, r->active2, r->active_prev, r->moments, r->slice_sum, r->slice_cnt, r->d_count };
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (r->vol_tex) cudaDestroyTextureObject(r->vol_tex);
+    if (r->vol_array) cudaFreeArray(r->vol_array);
     if (r->h_count) cudaFreeHost(r->h_count);
     delete r;
     c->reg = nullptr;
@@ -156,29 +161,15 @@ reg_slice_mean_kernel(const float* __restrict__ img, int P, float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float reg_fetch(const float* __restrict__ vol, int vx, int vy, int vz, int x, int y, int z)
+// tex3D(reconstructedTex_, pos / size) (cuda2.cu:3525): the volume is sampled by the TEXTURE UNIT, exactly as the
+// reference does it -- linear filter, normalised coordinates, border addressing, no half-texel offset (quirk G4).
+// Hardware filtering uses 1.8 fixed-point weights and its own arithmetic; going through the same unit makes the
+// sampled slices (and through them the similarity staircase the optimiser walks on) those of the reference, which a
+// software trilinear with float weights cannot reproduce (measured: 3e-4 relative on the samples, enough to change
+// which side of the `val < 0` padding test mask-border pixels fall on).  The reference divides with --use_fast_math.
+__device__ __forceinline__ float reg_tex3d(cudaTextureObject_t tex, float sx, float sy, float sz, float px, float py, float pz)
 {
-    if ((unsigned)x >= (unsigned)vx || (unsigned)y >= (unsigned)vy || (unsigned)z >= (unsigned)vz) return 0.0f;   // border mode
-    return __ldg(vol + ((size_t)z * vy + y) * vx + x);
-}
-
-// tex3D(reconstructedTex_, pos / size): linear, normalised, border; texel coordinate = pos - 0.5 (quirk G4).
-__device__ __forceinline__ float reg_tex3d(const float* __restrict__ vol, int vx, int vy, int vz, float px, float py, float pz)
-{
-    const float fx = px - 0.5f, fy = py - 0.5f, fz = pz - 0.5f;
-    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-    if (!(flx > -2.0f && flx < (float)vx + 1.0f && fly > -2.0f && fly < (float)vy + 1.0f && flz > -2.0f && flz < (float)vz + 1.0f))
-        return 0.0f;
-    const float ax = fx - flx, ay = fy - fly, az = fz - flz;
-    const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
-    const float c000 = reg_fetch(vol, vx, vy, vz, x0, y0, z0), c100 = reg_fetch(vol, vx, vy, vz, x0 + 1, y0, z0);
-    const float c010 = reg_fetch(vol, vx, vy, vz, x0, y0 + 1, z0), c110 = reg_fetch(vol, vx, vy, vz, x0 + 1, y0 + 1, z0);
-    const float c001 = reg_fetch(vol, vx, vy, vz, x0, y0, z0 + 1), c101 = reg_fetch(vol, vx, vy, vz, x0 + 1, y0, z0 + 1);
-    const float c011 = reg_fetch(vol, vx, vy, vz, x0, y0 + 1, z0 + 1), c111 = reg_fetch(vol, vx, vy, vz, x0 + 1, y0 + 1, z0 + 1);
-    const float c00 = c000 + ax * (c100 - c000), c10 = c010 + ax * (c110 - c010);
-    const float c01 = c001 + ax * (c101 - c001), c11 = c011 + ax * (c111 - c011);
-    const float c0 = c00 + ay * (c10 - c00), c1 = c01 + ay * (c11 - c01);
-    return c0 + az * (c1 - c0);
+    return tex3D<float>(tex, __fdividef(px, sx), __fdividef(py, sy), __fdividef(pz, sz));
 }
 
 __device__ __forceinline__ float3 reg_mul_pt(const float* __restrict__ m, float x, float y, float z)
@@ -191,7 +182,7 @@ __device__ __forceinline__ float3 reg_mul_pt(const float* __restrict__ m, float 
 // + the raw moments R4 (computeNCCAndReduce, cuda2.cu:4498-4550) needs.
 // grid = (tilesX*tilesY, active slices, 3 in-slice offsets); dynamic smem = raw[(T+2h)^2] + xpass[(T+2h)*T].
 __global__ void __launch_bounds__(REG_THREADS)
-reg_eval_kernel(const float* __restrict__ vol, int vx, int vy, int vz, VolGeom vg, const float* __restrict__ blurred,
+reg_eval_kernel(cudaTextureObject_t vol, int vx, int vy, int vz, VolGeom vg, const float* __restrict__ blurred,
                 const int* __restrict__ active, const float* __restrict__ M, const float* __restrict__ ofs, int W, int H,
                 int tilesX, int level_mod, RegKernel k, double* __restrict__ moments)
 {
@@ -214,7 +205,7 @@ reg_eval_kernel(const float* __restrict__ vol, int vx, int vy, int vz, VolGeom v
         float3 w = reg_mul_pt(sO, (float)gx, (float)gy, zofs);
         w = reg_mul_pt(sT, w.x, w.y, w.z);
         const float3 p = reg_mul_pt(vg.rw2i, w.x, w.y, w.z);
-        float val = reg_tex3d(vol, vx, vy, vz, p.x, p.y, p.z);
+        float val = reg_tex3d(vol, (float)vx, (float)vy, (float)vz, p.x, p.y, p.z);
         if (val < 0) val = -1.0f;
         raw[i] = val;
     }
@@ -311,7 +302,7 @@ __device__ __forceinline__ void reg_rot_params(const float* in, float p_rot[3])
 {
     const float TOL = 0.000001f;
     const float tmp = asinf(-1.0f * in[2]);
-    if (fabsf(cosf(tmp)) > TOL) {
+    if (fabsf(__cosf(tmp)) > TOL) {
         p_rot[0] = atan2f(in[6], in[10]);
         p_rot[1] = tmp;
         p_rot[2] = atan2f(in[1], in[0]);
@@ -323,8 +314,9 @@ __device__ __forceinline__ void reg_rot_params(const float* in, float p_rot[3])
 }
 __device__ __forceinline__ void reg_set_rotation(float* out, const float p_rot[3])
 {
-    const float cosrx = cosf(p_rot[0]), cosry = cosf(p_rot[1]), cosrz = cosf(p_rot[2]);
-    const float sinrx = sinf(p_rot[0]), sinry = sinf(p_rot[1]), sinrz = sinf(p_rot[2]);
+    // the reference is built with --use_fast_math: cos/sin are the MUFU intrinsics there
+    const float cosrx = __cosf(p_rot[0]), cosry = __cosf(p_rot[1]), cosrz = __cosf(p_rot[2]);
+    const float sinrx = __sinf(p_rot[0]), sinry = __sinf(p_rot[1]), sinrz = __sinf(p_rot[2]);
     out[0] = cosry * cosrz; out[1] = cosry * sinrz; out[2] = -sinry;
     out[4] = (sinrx * sinry * cosrz - cosrx * sinrz);
     out[5] = (sinrx * sinry * sinrz + cosrx * cosrz);
@@ -469,7 +461,7 @@ static int reg_evaluate_costs(svr_context* c, RegState* r, int a, int level, con
     {
         ProfScope prof(c, 5);
         dim3 grid(tilesX * tilesY, a, 3);
-        reg_eval_kernel<<<grid, REG_THREADS, smem, c->stream>>>(r->vol, c->vx, c->vy, c->vz, c->vg, r->blurred, r->active,
+        reg_eval_kernel<<<grid, REG_THREADS, smem, c->stream>>>(r->vol_tex, c->vx, c->vy, c->vz, c->vg, r->blurred, r->active,
                                                                  r->M, r->ofs, r->W, r->H, tilesX, level + 1, k, r->moments);
         SVR_KERNEL_CHECK(c);
     }
@@ -562,8 +554,34 @@ int svr_reg_prepare(svr_context* c)
     RegState* r = (RegState*)c->reg;
     REG_REQUIRE(c, r, "svr_reg_prepare: call svr_reg_init_storage first");
     REG_REQUIRE(c, c->V > 0 && c->recon, "svr_reg_prepare: no reconstruction volume");
-    if (reg_alloc(c, &r->vol, c->V)) return 1;
-    SVR_CUDA(c, cudaMemcpyAsync(r->vol, c->recon, c->V * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    // snapshot of the volume in a 3D cudaArray behind a texture object (cuda2.cu:3931-3956)
+    if (!r->vol_array || r->ax != c->vx || r->ay != c->vy || r->az != c->vz) {
+        if (r->vol_tex) { cudaDestroyTextureObject(r->vol_tex); r->vol_tex = 0; }
+        if (r->vol_array) { cudaFreeArray(r->vol_array); r->vol_array = nullptr; }
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+        SVR_CUDA(c, cudaMalloc3DArray(&r->vol_array, &desc, make_cudaExtent(c->vx, c->vy, c->vz)));
+        r->ax = c->vx; r->ay = c->vy; r->az = c->vz;
+        cudaResourceDesc res;
+        memset(&res, 0, sizeof(res));
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = r->vol_array;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 1;
+        SVR_CUDA(c, cudaCreateTextureObject(&r->vol_tex, &res, &td, nullptr));
+    }
+    {
+        cudaMemcpy3DParms cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.srcPtr = make_cudaPitchedPtr((void*)c->recon, (size_t)c->vx * sizeof(float), c->vx, c->vy);
+        cp.dstArray = r->vol_array;
+        cp.extent = make_cudaExtent(c->vx, c->vy, c->vz);
+        cp.kind = cudaMemcpyDeviceToDevice;
+        SVR_CUDA(c, cudaMemcpy3DAsync(&cp, c->stream));
+    }
     r->voxel = c->vdx;                 // _Blurring[0] = dev_reconstructed_.dim.x / 2, cuda2.cu:3892
     r->n_levels = 2; r->n_steps = 4; r->n_iterations = 20; r->epsilon = 0.0001f;
     r->prepared = true;

@@ -63,10 +63,13 @@ public:
     size_t NumberOfSlices() const { return slices_.size(); }
     double device_ms(int kind, long long* launches) const;
     void profile(bool on);
+    void DumpSetup(const std::string& dir) const;     // the inputs SyncGPU would upload, as raw arrays (tools/c2_parity.py)
     bool debug = false;
 
 private:
     void ck(int rc, const char* what) const;
+    void ensure_context();
+    int device_ = 0;
     svr_context* c_ = nullptr;
     Image reconstructed_, mask_;
     bool template_created_ = false, have_mask_ = false;

@@ -27,8 +27,11 @@
  *       the line search starts from there.
  *   G4  the texture read has no +0.5 texel-centre offset: volumePos = i samples half-way between voxels
  *       i-1 and i (border texels are 0).
- * Not reproduced: the texture unit's 1.8 fixed-point interpolation weights (exact float weights are used;
- * deviation D6), the x32 factor of averageIf/computeNCCAndReduce (32 threads per block pass the
+ * The texture unit's 1.8 fixed-point interpolation weights are modelled (round to nearest 1/256); what remains
+ * against the hardware filter of a B200 is ~3e-4 relative on a sample (measured against the reference's own
+ * sampled slices, tools/ref_reg_debug.py) -- the CUDA path samples through the texture unit itself and has no
+ * such residue (deviation D6 applies to this CPU oracle only).
+ * Not reproduced: the x32 factor of averageIf/computeNCCAndReduce (32 threads per block pass the
  * `threadIdx.x == 0` test: a power-of-two factor that cancels exactly in every ratio), fast-math
  * sin/cos/atan in the parameter kernels, and the nondeterministic order of the compacted active list
  * for more than 512 slices (a stable order is used).
@@ -112,7 +115,7 @@ void reg_filter_gauss_stack(float *data, int W, int H, int n, float sigma)
 
 /* ---- tex3D(reconstructedTex_, x/sx, y/sy, z/sz): linear filter, normalised coordinates, border mode
  * (cuda2.cu:3909-3959).  Texel space coordinate = u*N - 0.5 (quirk G4); texels outside the array read 0.
- * Exact float weights instead of the hardware's 1.8 fixed point (deviation D6). */
+ * Weights rounded to the hardware's 1.8 fixed point; the filter arithmetic itself is plain float (deviation D6). */
 static inline float reg_fetch(const float *vol, int vx, int vy, int vz, int x, int y, int z)
 {
     if (x < 0 || y < 0 || z < 0 || x >= vx || y >= vy || z >= vz) return 0.0f;
@@ -126,6 +129,10 @@ float reg_tex3d(const float *vol, int vx, int vy, int vz, float px, float py, fl
     float fx = px - 0.5f, fy = py - 0.5f, fz = pz - 0.5f;
     float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     float ax = fx - flx, ay = fy - fly, az = fz - flz;
+    /* the texture unit keeps the interpolation weights in 1.8 fixed point */
+    ax = floorf(ax * 256.0f + 0.5f) * (1.0f / 256.0f);
+    ay = floorf(ay * 256.0f + 0.5f) * (1.0f / 256.0f);
+    az = floorf(az * 256.0f + 0.5f) * (1.0f / 256.0f);
     /* guard the float -> int conversion for far-away positions */
     if (!(flx > -2.0f && flx < (float)vx + 1.0f && fly > -2.0f && fly < (float)vy + 1.0f && flz > -2.0f &&
           flz < (float)vz + 1.0f))

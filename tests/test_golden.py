@@ -2,7 +2,8 @@
 
 CPU: the oracle still reproduces them (regression pin; sums formed with OpenMP double atomics may differ in the
 last float bit).  GPU: the CUDA path reproduces them within the parity tolerances of test_gpu_parity.py.
-The reference itself holds no golden vectors for this path: "parity unpinned" (DESIGN.md section 4)."""
+The reference itself holds no golden vectors for this path; the vectors its own CUDA code produces on a B200 are in
+tests/golden/ref_*.npz and pinned by tests/test_ref_golden.py."""
 import importlib.util
 import os
 
@@ -66,12 +67,17 @@ def test_cuda_matches_svr_golden():
 
 @pytest.mark.gpu
 def test_cuda_matches_registration_golden():
+    """Oracle-generated golden: the oracle filters the volume in software, the CUDA path through the texture unit (as
+    the reference; tolerances explained in test_gpu_registration.py).  The tight comparison is the one against the
+    reference's own output in test_ref_golden.py."""
     from fetalreconstruction_b200.reconstruction import Reconstruction
-    got, gold = mg.reg_case(Reconstruction(0)), _load("reg_small")
-    assert np.abs(got["sim_level0"] - gold["sim_level0"]).max() <= 2e-5
-    assert np.abs(got["sim_level1"] - gold["sim_level1"]).max() <= 2e-5
-    d = np.abs(got["transforms_out"] - gold["transforms_out"]).reshape(len(gold["transforms_out"]), -1).max(1)
-    assert np.mean(d <= 1e-3) >= 0.75, d          # discrete optimiser decisions may flip (test_gpu_registration.py)
+    b = Reconstruction(0)
+    got, gold = mg.reg_case(b), _load("reg_small")
+    assert np.abs(got["sim_level0"] - gold["sim_level0"]).max() <= 4e-3
+    assert np.abs(got["sim_level1"] - gold["sim_level1"]).max() <= 4e-3
+    s_ours = b.evaluateCostsMultipleSlices(got["transforms_out"], 0)
+    s_gold = b.evaluateCostsMultipleSlices(gold["transforms_out"], 0)
+    assert s_ours.mean() >= s_gold.mean() - 0.01, (s_ours, s_gold)
 
 
 @pytest.mark.gpu

@@ -1,12 +1,12 @@
 """GPU: the fused registration path (svr_reg.cu through the C ABI) against oracle/reg_oracle.c.
 
-Tolerances.  The similarity is a ratio of mean-subtracted sums over ~1e3-1e4 pixels; the CUDA path forms the
-sums from double raw moments, the oracle from float products accumulated in double: |d similarity| <= 2e-5 is
-asserted (measured ~1e-6).  The optimiser takes discrete decisions on similarity differences against
-epsilon = 1e-4, so a transform can leave the oracle's trajectory when a comparison sits within rounding of
-the threshold; final transforms are therefore compared per parameter with a bulk bound (>= 80 % of the
-slices within 1e-3 mm / degrees) plus a loose bound on the rest, and the similarity-evaluation counts must
-agree within 10 %.
+Tolerances.  The CUDA path samples the volume through the texture unit, as the reference does (its similarity
+agrees with the reference's to 1.5e-6, tests/test_ref_golden.py); the oracle models the filter in software (1.8
+fixed-point weights, float arithmetic; deviation D6), which is ~3e-4 off per sample and can flip mask-border pixels
+across the `val < 0` padding test: |d similarity| <= 4e-3 is asserted (measured <= 1.5e-3; 5e-7 against the
+reference).  The optimiser takes discrete decisions on similarity differences against epsilon = 1e-4 and amplifies
+such differences, so the registered transforms are compared by the similarity they reach and by how far they moved,
+not parameter by parameter (the one-iteration parameter check against the reference is in test_ref_golden.py).
 """
 import numpy as np
 import pytest
@@ -62,7 +62,7 @@ def test_similarity_matches_oracle(inplane):
             t = feg.pack_transforms(tr)
             sg = g.evaluateCostsMultipleSlices(t, level)
             so = o.evaluateCostsMultipleSlices(t, level)
-            assert np.abs(sg - so).max() <= 2e-5, (level, np.abs(sg - so).max())
+            assert np.abs(sg - so).max() <= 4e-3, (level, np.abs(sg - so).max())
             assert np.abs(so).max() > 0.3
     # the per-level blur of the input slices
     bl = g.debugRegSlices(blurred=True)
@@ -80,10 +80,13 @@ def test_registration_matches_oracle_trajectory():
     to = o.registerSlicesToVolume(t0)
     pg = np.stack([rigid_parameters(m.reshape(4, 4).astype(np.float64)) for m in tg])
     po = np.stack([rigid_parameters(m.reshape(4, 4).astype(np.float64)) for m in to])
-    d = np.abs(pg - po).max(axis=1)
-    assert np.mean(d <= 1e-3) >= 0.8, d
-    assert d.max() <= 0.5, d
-    assert abs(g.reg_evaluations - o.reg_evaluations) <= 0.1 * o.reg_evaluations
+    p0 = np.stack([rigid_parameters(m.reshape(4, 4).astype(np.float64)) for m in t0])
+    # both optimisers move the slices by a comparable amount and end at a comparable similarity
+    assert np.median(np.abs(pg - po).max(axis=1)) <= max(np.median(np.abs(po - p0).max(axis=1)), 0.05)
+    sg = g.evaluateCostsMultipleSlices(tg, 0)
+    so = g.evaluateCostsMultipleSlices(to, 0)
+    assert sg.mean() >= so.mean() - 0.01, (sg, so)
+    assert abs(g.reg_evaluations - o.reg_evaluations) <= 0.25 * o.reg_evaluations
     # it actually moved the slices, towards higher similarity
     assert np.abs(tg - t0).max() > 1e-3
     s0 = g.evaluateCostsMultipleSlices(t0, 0)
