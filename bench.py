@@ -169,6 +169,26 @@ def run_cpu_baseline(cfg, steps=1, warmup=0):
                       f"{t:.1f} s per step; oracle/svr_oracle.c with OpenMP"}, t
 
 
+def run_reference_cuda(cfg, stacks=1):
+    """The reference's OWN CUDA path (oracle/_ref: its unmodified sources recompiled for sm_100a) timed on this box's GPU on a
+    bounded sample of the workload: `stacks` whole stacks, one outer iteration (the same 10 slice-projections per slice).
+    Runs in a subprocess (the reference resets the device and keeps process-global state).  A reported baseline."""
+    if cfg.name != "C3" or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_cuda2.so")):
+        return None
+    tool = os.path.join(ROOT, "tools", "ref_bench.py")
+    try:
+        subprocess.run([sys.executable, tool, "gen", "--stacks", str(stacks)], check=True, capture_output=True, text=True, timeout=300)
+        r = subprocess.run([sys.executable, tool, "ref", "--rec-iters", "4"], check=True, capture_output=True, text=True, timeout=600)
+        line = [l for l in r.stdout.splitlines() if l.startswith("REFBENCH_JSON ")][-1]
+        d = json.loads(line[len("REFBENCH_JSON "):])
+    except Exception as e:                                   # the baseline is optional; the bench line is not
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    return {"value": d["S"] * PROJ_PER_SLICE_STEP / d["iteration_s"], "unit": UNIT, "kind": "reference CUDA path on this GPU",
+            "sample": f"{d['S']} slices ({stacks} stack(s) of the C3 workload, full 256^3 volume), one outer iteration, "
+                      f"{d['iteration_s']:.3f} s wall; every call synchronous as in the reference",
+            "ms_per_call": {k: round(v, 3) for k, v in d["ms_per_call"].items() if v >= 0.05}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,8 +200,10 @@ def run_reference(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_json(cfg, args.gpus), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "the reference cannot be compiled here (SURVEY.md 8c): this arm times the oracle port of its "
-                    "CUDA algorithm on the host cores; warm-up capped at 1 step (deterministic CPU code)"}
+            "note": "the reference's IRTK/TBB CPU path cannot be compiled here (Boost/TBB/GSL absent, SURVEY.md 8c): this arm "
+                    "times the oracle port of its algorithm on the host cores; warm-up capped at 1 step (deterministic CPU "
+                    "code).  The reference's own CUDA path does compile (oracle/_ref) and is reported by the main arm as "
+                    "`reference_cuda`."}
     print(json.dumps(line))
 
 
@@ -196,6 +218,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-registration", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -367,12 +390,15 @@ def main():
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base, _ = run_cpu_baseline(cfg, steps=1, warmup=0)
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_reference_cuda:
+        ref_cuda = run_reference_cuda(cfg)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_json(cfg, world),
-                "volumes_per_hour": vph, "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
+                "volumes_per_hour": vph, "roofline": roofline, "cpu_baseline": base, "reference_cuda": ref_cuda, "e2e": e2e,
                 "registration": registration, "gpu_launches": int(ln.item()), "clocks": clocks}
         print(json.dumps(line))
     if world > 1:

@@ -52,7 +52,7 @@ struct RegState {
     int* active = nullptr;        // dev_active_slices
     int* active2 = nullptr;
     int* active_prev = nullptr;
-    double* moments = nullptr;    // [S][3][8]
+    double* moments = nullptr;    // [S][3][tiles][8]: per-CTA partial moments, summed in a fixed order (deterministic)
     float* slice_sum = nullptr;   // per-level sum / count of the blurred input slices (averageIf on layersA)
     int* slice_cnt = nullptr;
     int* d_count = nullptr;       // dev_active_slice_count
@@ -255,7 +255,9 @@ reg_eval_kernel(cudaTextureObject_t vol, int vx, int vy, int vz, VolGeom vg, con
     if (threadIdx.x < 8) {
         double v = 0;
         for (int w = 0; w < REG_THREADS / 32; ++w) v += red[w][threadIdx.x];
-        if (v != 0.0) atomicAdd(&moments[((size_t)t * 3 + o) * 8 + threadIdx.x], v);
+        // one slot per CTA, reduced in a fixed order by reg_finish_kernel: the similarity (and so the optimiser's
+        // trajectory) is bit-reproducible from run to run, which a float/double atomic accumulation is not
+        moments[(((size_t)t * 3 + o) * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = v;
     }
 }
 
@@ -263,12 +265,24 @@ reg_eval_kernel(cudaTextureObject_t vol, int vx, int vy, int vz, VolGeom vg, con
 // literally: per active index t the NCC accumulator lives at tf[2a+t], the triplet at tf[3a+3t..], and
 // between offsets the reference clears tf[2S, 5S) (quirk G1); sum/count of the sampled slice accumulate
 // over the offsets (quirk G2).
-__global__ void reg_finish_kernel(int a, int S, const int* __restrict__ active, const double* __restrict__ moments,
+__global__ void reg_finish_kernel(int a, int S, int tiles, const int* __restrict__ active, const double* __restrict__ moments,
                                   const float* __restrict__ slice_sum, const int* __restrict__ slice_cnt,
                                   float* __restrict__ sim, int writeoffset, int writestep, int writenum)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+{   // one warp per active slice
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= a) return;
+    // fixed-order sum of the per-CTA partial moments: lanes stride over the tiles, then a butterfly
+    double mo[3][8];
+#pragma unroll
+    for (int o = 0; o < 3; ++o)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double v = 0.0;
+            for (int tl = lane; tl < tiles; tl += 32) v += moments[(((size_t)t * 3 + o) * tiles + tl) * 8 + q];
+            for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+            mo[o][q] = v;
+        }
+    if (lane != 0) return;
     const int slice = active[t];
     float avg_a = slice_sum[slice];
     if (avg_a != 0) avg_a /= slice_cnt[slice];
@@ -276,8 +290,9 @@ __global__ void reg_finish_kernel(int a, int S, const int* __restrict__ active, 
     float trip[3] = { 0.f, 0.f, 0.f };
     float acc = 0.f;
     const int zlo = 2 * S, zhi = 5 * S;
+#pragma unroll
     for (int o = 0; o < 3; ++o) {
-        const double* m = moments + ((size_t)t * 3 + o) * 8;
+        const double* m = mo[o];
         cum_sb += (float)m[7];
         cum_nb += (int)m[6];
         if (2 * a + t >= zlo && 2 * a + t < zhi) acc = 0.f;
@@ -454,7 +469,6 @@ static int reg_evaluate_costs(svr_context* c, RegState* r, int a, int level, con
                               int writestep, int writenum)
 {   // evaluateCostsMultipleSlices, cuda2.cu:4150-4221
     if (a == 0) return 0;
-    SVR_CUDA(c, cudaMemsetAsync(r->moments, 0, sizeof(double) * 24 * (size_t)a, c->stream));
     const int tilesX = cdiv(r->W, REG_TILE), tilesY = cdiv(r->H, REG_TILE);
     const int h = k.K - 1, TW = REG_TILE + 2 * h;
     const size_t smem = sizeof(float) * ((size_t)TW * TW + (size_t)TW * REG_TILE);
@@ -465,7 +479,7 @@ static int reg_evaluate_costs(svr_context* c, RegState* r, int a, int level, con
                                                                  r->M, r->ofs, r->W, r->H, tilesX, level + 1, k, r->moments);
         SVR_KERNEL_CHECK(c);
     }
-    reg_finish_kernel<<<cdiv(a, 128), 128, 0, c->stream>>>(a, r->S, r->active, r->moments, r->slice_sum, r->slice_cnt, r->sim,
+    reg_finish_kernel<<<cdiv(a, 4), 128, 0, c->stream>>>(a, r->S, tilesX * tilesY, r->active, r->moments, r->slice_sum, r->slice_cnt, r->sim,
                                                            writeoffset, writestep, writenum);
     SVR_KERNEL_CHECK(c);
     r->evals += 3LL * a;
@@ -508,7 +522,7 @@ int svr_reg_init_storage(svr_context* c, int W, int H, int S, float dx, float dy
         reg_alloc(c, &r->ofs, 16 * Sn) || reg_alloc(c, &r->res_i2w, 16 * Sn) || reg_alloc(c, &r->M, 16 * Sn) ||
         reg_alloc(c, &r->Morig, 16 * Sn) || reg_alloc(c, &r->sim, 5 * Sn) || reg_alloc(c, &r->grad, 7 * Sn) ||
         reg_alloc(c, &r->active, Sn) || reg_alloc(c, &r->active2, Sn) || reg_alloc(c, &r->active_prev, Sn) ||
-        reg_alloc(c, &r->moments, 24 * Sn) || reg_alloc(c, &r->slice_sum, Sn) || reg_alloc(c, &r->slice_cnt, Sn) ||
+        reg_alloc(c, &r->moments, 24 * Sn * (size_t)(cdiv(W, REG_TILE) * cdiv(H, REG_TILE))) || reg_alloc(c, &r->slice_sum, Sn) || reg_alloc(c, &r->slice_cnt, Sn) ||
         reg_alloc(c, &r->d_count, 1))
         return 1;
     SVR_CUDA(c, cudaMallocHost((void**)&r->h_count, sizeof(int)));

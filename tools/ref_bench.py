@@ -100,10 +100,14 @@ def run_arm(arm, out, rec_iters):
     iter_s = time.perf_counter() - t0 - cap
     res.update(volume=raw.syncCPU(), scale=p._scale, slice_weight=p._slice_weight, em=np.array([p._sigma, p._mix, p._m], np.float64),
                times=json.dumps({k: v for k, v in b.times.items()}), setup_s=setup_s, iter_s=iter_s, S=ds.S)
-    np.savez(out, **res)
+    if out:
+        np.savez(out, **res)
     print(arm, "S", ds.S, "setup %.2fs iteration %.2fs" % (setup_s, iter_s))
     for k, (t, n) in sorted(b.times.items(), key=lambda kv: -kv[1][0]):
         print(f"  {k:40s} {n:3d} calls {1e3 * t / n:10.2f} ms/call")
+    # one machine-readable line for bench.py
+    print("REFBENCH_JSON " + json.dumps({"arm": arm, "S": int(ds.S), "rec_iters": rec_iters, "iteration_s": iter_s, "setup_s": setup_s,
+                                         "ms_per_call": {k: 1e3 * t / n for k, (t, n) in b.times.items()}}))
 
 
 def stats(a, b):
