@@ -7,10 +7,12 @@
 // One cost evaluation in the reference = per in-slice offset: resample kernel -> 2 Gauss kernels ->
 // averageIf -> memset -> NCC kernel -> addNcc, i.e. 19 launches and 5 full passes over a materialised
 // slice stack (~24 B per pixel per offset).  Here it is ONE kernel over (tile, active slice, offset):
-//   sample the volume at a 32x32 pixel tile plus the blur halo (software trilinear, border = 0, the
-//   reference's missing half-texel offset reproduced) -> separable Gauss in shared memory with the
-//   reference's padding rules -> raw moments {n, Sa, Sb, Sab, Saa, Sbb} over the NCC domain plus {count,
-//   sum} of the sampled slice, accumulated in double, warp-shuffle + block reduce, 8 double atomics per CTA.
+//   sample the volume at a 32x32 pixel tile plus the blur halo through the TEXTURE UNIT (3D cudaArray, linear
+//   filter, border addressing, normalised coordinates without the half-texel offset: the reference's own fetch,
+//   so the samples are the reference's bit for bit up to the float position) -> separable Gauss in shared memory
+//   with the reference's padding rules -> raw moments {n, Sa, Sb, Sab, Saa, Sbb} over the NCC domain plus {count,
+//   sum} of the sampled slice, accumulated in double, warp-shuffle + block reduce, one slot of 8 doubles per CTA
+//   summed in a fixed order by the finishing kernel (bit-reproducible similarities).
 // The sampled slice is never written to memory: algorithmic traffic is the 4 B read of the blurred input
 // slice per pixel per offset plus the (L2-resident) volume gather.  A finishing kernel (1 thread per
 // active slice) turns the raw moments into the reference's mean-subtracted sums and replays the
