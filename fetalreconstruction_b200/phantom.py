@@ -98,10 +98,18 @@ def _phantom_at(world: torch.Tensor, centres, radii, amps) -> torch.Tensor:
     return out
 
 
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous balanced share [lo, hi) of n items for `rank` of `world`."""
+    return rank * n // world, (rank + 1) * n // world
+
+
 def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: bool = True,
-                 stacks: range | None = None) -> Dataset:
+                 stacks: range | None = None, shard: tuple[int, int] | None = None) -> Dataset:
     """`stacks` restricts generation to a contiguous range of stacks (a rank's shard); every stack is
-    seeded on its own, so the slices are identical however the stacks are sharded."""
+    seeded on its own, so the slices are identical however the stacks are sharded.
+    `shard = (rank, world)` instead gives the rank the rank-th contiguous 1/world of the slices of EVERY stack:
+    every rank then sees the same mix of orientations (the per-slice cost of the PSF kernels depends on it), so the
+    ranks are balanced by construction.  Every slice is seeded by its own (stack, index) either way."""
     rng = np.random.default_rng(cfg.seed)
     vx, vy, vz = cfg.vol_size
     vol_attr = ImageAttributes(vx, vy, vz, cfg.vol_voxel, cfg.vol_voxel, cfg.vol_voxel)
@@ -127,7 +135,8 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
     Nx, Ny = cfg.slice_size
     thickness = cfg.thickness if cfg.thickness is not None else 2.0 * cfg.spacing
     stacks = range(cfg.n_stacks) if stacks is None else stacks
-    S = len(stacks) * cfg.slices_per_stack
+    j_lo, j_hi = shard_bounds(cfg.slices_per_stack, *shard) if shard is not None else (0, cfg.slices_per_stack)
+    S = len(stacks) * (j_hi - j_lo)
     slices = np.empty((S, Ny, Nx), np.float32)
     i2w = np.empty((S, 16), np.float32)
     w2i = np.empty((S, 16), np.float32)
@@ -160,6 +169,9 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
             sa = stack_attr.slice_attributes(j, thickness)
             A, Ainv = sa.image_to_world(), sa.world_to_image()
             tpar = np.concatenate([mrng.normal(0, cfg.motion_mm, 3), mrng.normal(0, cfg.motion_deg, 3)])
+            corrupt = srng.uniform() < cfg.corrupt_fraction
+            if not (j_lo <= j < j_hi):                 # the random streams advance for every slice of the stack
+                continue
             T_true = rigid_matrix(*tpar)
             T_used = T_true if perfect_registration else np.eye(4)
             # acquisition: sample the phantom where the (moved) slice really was
@@ -169,7 +181,7 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
             if cfg.noise > 0:
                 g = torch.Generator(device="cpu").manual_seed(cfg.seed * 131 + st * cfg.slices_per_stack + j)
                 val = val + cfg.noise * torch.randn(val.shape, generator=g).to(dev)
-            if srng.uniform() < cfg.corrupt_fraction:
+            if corrupt:
                 val = val * 0.3
             # MaskSlices: centre maps (rounded) outside the mask / onto mask 0 -> -1; <0.01 -> -1
             Mu = torch.as_tensor(T_used @ A, dtype=torch.float32, device=dev)
