@@ -104,7 +104,7 @@ int svr_destroy(svr_context* c)
     dev_free(&c->mask_f); dev_free(&c->mask_u8); dev_free(&c->acc2); dev_free(&c->pack2);
     dev_free(&c->slices); dev_free(&c->slices_restore); dev_free(&c->weights); dev_free(&c->simslices);
     dev_free(&c->simweights); dev_free(&c->siminside); dev_free(&c->psf_sums); dev_free(&c->voxel_flag);
-    dev_free(&c->valid_idx); dev_free(&c->slice_count); dev_free(&c->slice_inside); dev_free(&c->scales);
+    dev_free(&c->valid_idx); dev_free(&c->pair_idx); dev_free(&c->slice_count); dev_free(&c->slice_inside); dev_free(&c->scales);
     dev_free(&c->scales_mstep); dev_free(&c->slice_weights); dev_free(&c->slice_tmp); dev_free(&c->geom);
     dev_free(&c->mats); dev_free(&c->dims); dev_free(&c->partials);
     svr_reg_free(c);
@@ -224,7 +224,7 @@ int svr_init_storage_volumes(svr_context* c, int Nx, int Ny, int S)
     const size_t NP = c->NP, Sn = (size_t)std::max(S, 1);
     if (dev_alloc(c, &c->slices, NP) || dev_alloc(c, &c->slices_restore, NP) || dev_alloc(c, &c->weights, NP) ||
         dev_alloc(c, &c->simslices, NP) || dev_alloc(c, &c->simweights, NP) || dev_alloc(c, &c->siminside, NP) ||
-        dev_alloc(c, &c->psf_sums, NP) || dev_alloc(c, &c->voxel_flag, NP) || dev_alloc(c, &c->valid_idx, NP) ||
+        dev_alloc(c, &c->psf_sums, NP) || dev_alloc(c, &c->voxel_flag, NP) || dev_alloc(c, &c->valid_idx, NP) || dev_alloc(c, &c->pair_idx, (size_t)std::max(S, 1) * Ny * ((Nx + 1) / 2)) ||
         dev_alloc(c, &c->slice_count, Sn) || dev_alloc(c, &c->slice_inside, Sn) || dev_alloc(c, &c->scales, Sn) ||
         dev_alloc(c, &c->scales_mstep, Sn) || dev_alloc(c, &c->slice_weights, Sn) || dev_alloc(c, &c->slice_tmp, 4 * Sn) ||
         dev_alloc(c, &c->geom, Sn) || dev_alloc(c, &c->mats, 4 * 16 * Sn) || dev_alloc(c, &c->dims, 3 * Sn))
@@ -246,6 +246,7 @@ int svr_init_storage_volumes(svr_context* c, int Nx, int Ny, int S)
     c->h_scales.assign(S, 1.0f);
     c->h_slice_weights.assign(S, 1.0f);
     c->n_valid = 0;
+    c->n_pairs = 0;
     c->have_mats = c->have_dims = false;
     SVR_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;

@@ -200,6 +200,39 @@ __device__ __forceinline__ void psf_rows(const SliceGeom& g, const VolGeom& vg, 
     }
 }
 
+// One x-row of accepted PSF values (0 where the epsilon-skip rejects a tap): the inner loop of psf_rows for callers
+// that place the row themselves (the paired scatter).  (rx, ry, rz) = PSF-unit position of the row's tap with ox = 0.
+template <class TR, bool RECUR>
+__device__ __forceinline__ void psf_row_values(const SliceGeom& g, float rx, float ry, float rz, float (&p)[TR::SUP])
+{
+    const float bx0 = g.bx[0], by0 = g.by[0], bz0 = g.bz[0];
+    const float two_b = g.two_b, bb = g.bb, kappa = g.kappa;
+    constexpr int HALF = TR::SUP / 2;
+    float old = FLT_MAX;
+    float gz = 0.f, rho = 0.f;
+#pragma unroll
+    for (int i = 0; i < TR::SUP; ++i) {
+        const float fox = (float)(i - TR::CEN);
+        float gauss;
+        if (RECUR) {
+            if (i % HALF == 0) {
+                const float dz = fmaf(fox, bz0, rz);
+                gz = ex2_approx(-(dz * dz));
+                rho = ex2_approx(-fmaf(two_b, dz, bb));
+            }
+            gauss = gz;
+            if (i % HALF != HALF - 1) { gz *= rho; rho *= kappa; }
+        } else {
+            const float dz = fmaf(fox, bz0, rz);
+            gauss = ex2_approx(-(dz * dz));
+        }
+        const float psf = sinc2_eval(fmaf(fox, bx0, rx), fmaf(fox, by0, ry)) * gauss;
+        const bool accept = TR::accept(old, psf);
+        old = accept ? psf : old;
+        p[i] = accept ? psf : 0.0f;
+    }
+}
+
 // Dispatch on the (per-thread) interior flag and the (per-slice) recurrence flag.
 template <class TR, class Tap, class RowEnd>
 __device__ __forceinline__ void psf_rows_dispatch(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, Tap&& tap,

@@ -40,6 +40,8 @@ struct svr_context {
     unsigned char* voxel_flag = nullptr; // dev_sliceVoxel_count_ (0/1)
     uint32_t* valid_idx = nullptr; // compacted indices of pixels != -1 (static after FillSlices)
     uint32_t n_valid = 0;
+    uint32_t* pair_idx = nullptr;  // even-x pixels (x, x+1) of which at least one is != -1: the units of the paired scatter
+    uint32_t n_pairs = 0;
     int* slice_count = nullptr;    // [S] per-slice voxel_num (deviation D4)
     int* slice_inside = nullptr;   // [S] OR of siminside since the last Gaussian reconstruction
     float* scales = nullptr;       // dev_d_scales: what the kernels see

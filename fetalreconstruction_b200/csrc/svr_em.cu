@@ -457,6 +457,17 @@ struct NotPadding {
     const float* s;
     __device__ bool operator()(uint32_t i) const { return s[i] != -1.0f; }
 };
+// even-x pixel e such that e or e + 1 (same slice row) is valid: one unit of the paired scatter (svr_psf.cu)
+struct PairHead {
+    const float* s;
+    uint32_t Nx;
+    __device__ bool operator()(uint32_t i) const
+    {
+        const uint32_t x = i % Nx;
+        if (x & 1u) return false;
+        return s[i] != -1.0f || (x + 1 < Nx && s[i + 1] != -1.0f);
+    }
+};
 int svr_launch_compact_valid(svr_context* c)
 {
     thrust::counting_iterator<uint32_t> it(0);
@@ -475,6 +486,18 @@ int svr_launch_compact_valid(svr_context* c)
     SVR_CUDA(c, cudaMemcpyAsync(&h, d_num, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     SVR_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_valid = (uint32_t)h;
+    PairHead ph{ c->slices, (uint32_t)c->Nx };
+    SVR_CUDA(c, cub::DeviceSelect::If(nullptr, need, it, c->pair_idx, d_num, (int)c->NP, ph, c->stream));
+    if (need > c->cub_tmp_bytes) {
+        if (c->cub_tmp) cudaFree(c->cub_tmp);
+        SVR_CUDA(c, cudaMalloc(&c->cub_tmp, need));
+        c->cub_tmp_bytes = need;
+    }
+    SVR_CUDA(c, cub::DeviceSelect::If(c->cub_tmp, need, it, c->pair_idx, d_num, (int)c->NP, ph, c->stream));
+    c->launches += 2;
+    SVR_CUDA(c, cudaMemcpyAsync(&h, d_num, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_pairs = (uint32_t)h;
     return 0;
 }
 

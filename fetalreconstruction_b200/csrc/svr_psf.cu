@@ -23,6 +23,10 @@
 #ifndef SVR_MINB
 #define SVR_MINB 5
 #endif
+// The paired scatter keeps two pixel states and a 2 x 18-voxel row accumulator in registers.
+#ifndef SVR_MINB_PAIR
+#define SVR_MINB_PAIR 3
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Per-slice geometry (runs when matrices or voxel sizes change; S threads).
@@ -106,6 +110,118 @@ __device__ __forceinline__ void red_row_paired(float2* __restrict__ acc2, int v0
         if (u + w > 0.0f)                                  // psf >= 0: skip all-zero pairs (and NaNs)
             atomicAdd(base + m, make_float4(u * a, u * c, w * a, w * c));
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Paired scatter.  The scatter kernels are bound by the rate of global reductions (measured: half the REDs = half the
+// kernel time), and two neighbouring pixels of a slice write almost the same voxels: their 16^3 supports are offset by
+// d = centre(B) - centre(A), usually one voxel along one axis.  A thread therefore takes TWO consecutive valid pixels,
+// walks the UNION of their supports volume-row by volume-row, sums both pixels' contributions to a row in registers
+// (20 voxels: 16 + |d.x| + alignment) and flushes the row once: ~10 vector reductions per row pair instead of 18.
+// Exact: the per-pixel tap values, the epsilon-skip chains and the set of (voxel, value) contributions are unchanged,
+// only the order in which floats meet in the accumulator differs (as with any atomic scatter, Q8).
+// The pairs are the pixels (x, x + 1) with x even of one slice row (svr_launch_compact_valid builds the list of even
+// positions where at least one of the two is valid): a pair never straddles rows or slices, and a lone pixel runs
+// the same code with its partner switched off, so a warp has ONE code path.  Handled here: both pixels interior and
+// |d.x| <= 2 (any d.y, d.z); anything else (mask touching the volume faces, very coarse pixels) takes the one-pixel path.
+struct PairWeights { float aA, cA, aB, cB; };     // {numerator, denominator} scale of pixel A and of pixel B
+
+constexpr int PAIR_SLACK = 4;                     // row accumulator = SUP + 4 voxels: |d.x| <= 2 plus one for the alignment
+
+// Adds p[0..SUP) * (a, c) into (qn, qd) at element offset s in {0, 1, 2, 3}.
+template <int SUP>
+__device__ __forceinline__ void pair_accumulate(float (&qn)[SUP + PAIR_SLACK], float (&qd)[SUP + PAIR_SLACK], const float (&p)[SUP], int s,
+                                                float a, float c)
+{
+    const bool s1 = (s & 1) != 0, s2 = (s & 2) != 0;
+    float t[SUP + 1];                              // shift by the low bit
+    t[0] = s1 ? 0.0f : p[0];
+#pragma unroll
+    for (int j = 1; j < SUP; ++j) t[j] = s1 ? p[j - 1] : p[j];
+    t[SUP] = s1 ? p[SUP - 1] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < SUP + 3; ++j) {            // shift by two
+        const float lo = j < SUP + 1 ? t[j] : 0.0f;
+        const float hi = j >= 2 ? t[j - 2] : 0.0f;
+        const float v = s2 ? hi : lo;
+        qn[j] = fmaf(v, a, qn[j]);
+        qd[j] = fmaf(v, c, qd[j]);
+    }
+}
+
+// MASKFLAG: also report, per pixel, whether an accepted tap landed on a voxel with mask != 0 (K1's sliceVoxel_count).
+template <class TR, bool RECUR, bool MASKFLAG>
+__device__ __forceinline__ void scatter_pair(const SliceGeom& g, const VolGeom& vg, const PixelSetup& A, const PixelSetup& B,
+                                             bool liveA, bool liveB, const PairWeights w, float2* __restrict__ acc2,
+                                             const unsigned char* __restrict__ mask, bool& anyA, bool& anyB)
+{
+    constexpr int SUP = TR::SUP, CEN = TR::CEN, HI = TR::SUP - 1 - TR::CEN;
+    const int vx = vg.vx, vy = vg.vy;
+    const float bx1 = g.bx[1], by1 = g.by[1], bz1 = g.bz[1];
+    const float bx2 = g.bx[2], by2 = g.by[2], bz2 = g.bz[2];
+    // bounds of the union of the live supports (a dead pixel takes its partner's centre)
+    const int czA = liveA ? A.cz : B.cz, czB = liveB ? B.cz : A.cz;
+    const int cyA = liveA ? A.cy : B.cy, cyB = liveB ? B.cy : A.cy;
+    const int cxA = liveA ? A.cx : B.cx, cxB = liveB ? B.cx : A.cx;
+    const int zlo = min(czA, czB) - CEN, zhi = max(czA, czB) + HI;
+    const int ylo = min(cyA, cyB) - CEN, yhi = max(cyA, cyB) + HI;
+    const int xmin = min(cxA, cxB) - CEN;
+#pragma unroll 1
+    for (int Z = zlo; Z <= zhi; ++Z) {
+        const int ozA = Z - A.cz, ozB = Z - B.cz;
+        const bool zA = liveA && (unsigned)(ozA + CEN) < (unsigned)SUP, zB = liveB && (unsigned)(ozB + CEN) < (unsigned)SUP;
+        const float fzA = (float)ozA, fzB = (float)ozB;
+        const float zxA = fmaf(fzA, bx2, A.ex), zyA = fmaf(fzA, by2, A.ey), zzA = fmaf(fzA, bz2, A.ez);
+        const float zxB = fmaf(fzB, bx2, B.ex), zyB = fmaf(fzB, by2, B.ey), zzB = fmaf(fzB, bz2, B.ez);
+#pragma unroll 1
+        for (int Y = ylo; Y <= yhi; ++Y) {
+            const int oyA = Y - A.cy, oyB = Y - B.cy;
+            const bool okA = zA && (unsigned)(oyA + CEN) < (unsigned)SUP;
+            const bool okB = zB && (unsigned)(oyB + CEN) < (unsigned)SUP;
+            if (!okA && !okB) continue;
+            const int rowbase = (Z * vy + Y) * vx;
+            const int x0 = xmin - ((rowbase + xmin) & 1);          // even accumulator index: 16-byte aligned pairs
+            float qn[SUP + PAIR_SLACK], qd[SUP + PAIR_SLACK];      // voxels x0 .. x0 + SUP + 3
+#pragma unroll
+            for (int j = 0; j < SUP + PAIR_SLACK; ++j) { qn[j] = 0.f; qd[j] = 0.f; }
+            float p[SUP];
+            if (okA) {
+                const float foy = (float)oyA;
+                psf_row_values<TR, RECUR>(g, fmaf(foy, bx1, zxA), fmaf(foy, by1, zyA), fmaf(foy, bz1, zzA), p);
+                if (MASKFLAG) {
+                    const int v0 = rowbase + A.cx - CEN;
+#pragma unroll
+                    for (int i = 0; i < SUP; ++i) if (p[i] != 0.0f && mask[v0 + i]) anyA = true;
+                }
+                pair_accumulate<SUP>(qn, qd, p, A.cx - CEN - x0, w.aA, w.cA);
+            }
+            if (okB) {
+                const float foy = (float)oyB;
+                psf_row_values<TR, RECUR>(g, fmaf(foy, bx1, zxB), fmaf(foy, by1, zyB), fmaf(foy, bz1, zzB), p);
+                if (MASKFLAG) {
+                    const int v0 = rowbase + B.cx - CEN;
+#pragma unroll
+                    for (int i = 0; i < SUP; ++i) if (p[i] != 0.0f && mask[v0 + i]) anyB = true;
+                }
+                pair_accumulate<SUP>(qn, qd, p, B.cx - CEN - x0, w.aB, w.cB);
+            }
+            float4* base = reinterpret_cast<float4*>(acc2 + (rowbase + x0));
+#pragma unroll
+            for (int m = 0; m < (SUP + PAIR_SLACK) / 2; ++m) {
+                const float4 r = make_float4(qn[2 * m], qd[2 * m], qn[2 * m + 1], qd[2 * m + 1]);
+                if (r.y + r.w > 0.0f) atomicAdd(base + m, r);       // denominators are psf * c with c > 0: skips all-zero pairs (and NaNs)
+            }
+        }
+    }
+}
+
+// Which path a pair takes: 0 = nothing live, 1 = scatter_pair, 2 = one-pixel path(s).
+__device__ __forceinline__ int pair_mode(const PixelSetup& a, const PixelSetup& b, bool liveA, bool liveB)
+{
+    if (!liveA && !liveB) return 0;
+    if ((liveA && !a.interior) || (liveB && !b.interior)) return 2;
+    if (liveA && liveB && abs(a.cx - b.cx) > 2) return 2;
+    return 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,32 +350,31 @@ int svr_launch_simulate(svr_context* c)
 
 // ---------------------------------------------------------------------------------------------
 // K3: SuperresolutionKernel3D_tex (reconstruction_cuda2.cu:408-522).
+// Per-pixel inputs of K3: false when the pixel contributes nothing (no PSF mass or zero weight).
 template <class TR>
-__global__ void __launch_bounds__(128, SVR_MINB)
-superres_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
-                        const float* __restrict__ slices, const float* __restrict__ weights,
-                        const float* __restrict__ simslices, const float* __restrict__ slice_weights,
-                        const float* __restrict__ scales, const SliceGeom* __restrict__ geom, VolGeom vg,
-                        const float* __restrict__ psf_sums, float2* __restrict__ acc2)
+__device__ __forceinline__ bool superres_pixel(uint32_t idx, int Nx, int P, const float* __restrict__ slices,
+                                               const float* __restrict__ weights, const float* __restrict__ simslices,
+                                               const float* __restrict__ slice_weights, const float* __restrict__ scales,
+                                               const float* __restrict__ psf_sums, int& k, int& x, int& y, float& aw, float& cw)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_valid) return;
-    const uint32_t idx = valid_idx[t];
     const float sume = psf_sums[idx];
-    if (sume == 0.0f) return;
-    const int k = idx / P, pix = idx - k * P;
-    const int y = pix / Nx, x = pix - y * Nx;
-    const SliceGeom& g = geom[k];
-
+    if (sume == 0.0f) return false;
+    k = idx / P;
+    const int pix = idx - k * P;
+    y = pix / Nx; x = pix - y * Nx;
     const float w = weights[idx];
     const float ss = simslices[idx];
     float sliceVal = slices[idx] * scales[k];
     sliceVal = (ss > 0.0f) ? (sliceVal - ss) : 0.0f;
-    const float cw = w * slice_weights[k] / sume;      // psf/sume * w * slice_weight
-    const float aw = cw * sliceVal;
-    // A pixel with zero weight adds exact zeros everywhere: skip its 4096 taps.
-    if (cw == 0.0f) return;
-    const PixelSetup ps = pixel_setup<TR>(g, vg, x, y);
+    cw = w * slice_weights[k] / sume;               // psf/sume * w * slice_weight
+    aw = cw * sliceVal;
+    return cw != 0.0f;                              // a pixel with zero weight adds exact zeros everywhere: skip its taps
+}
+
+template <class TR>
+__device__ __forceinline__ void superres_single(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, float aw, float cw,
+                                                float2* __restrict__ acc2)
+{
     if (ps.interior) {
         float p[TR::SUP];
         auto tap = [&](int i, float psf, bool, int) { p[i] = psf; };
@@ -273,17 +388,53 @@ superres_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx
     }
 }
 
+// One thread = one pixel pair (see scatter_pair); pair_idx[t] = linear index of the pair's even-x pixel.
+template <class TR>
+__global__ void __launch_bounds__(128, SVR_MINB_PAIR)
+superres_scatter_kernel(uint32_t n_pairs, const uint32_t* __restrict__ pair_idx, int Nx, int P,
+                        const float* __restrict__ slices, const float* __restrict__ weights,
+                        const float* __restrict__ simslices, const float* __restrict__ slice_weights,
+                        const float* __restrict__ scales, const SliceGeom* __restrict__ geom, VolGeom vg,
+                        const float* __restrict__ psf_sums, float2* __restrict__ acc2)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    const uint32_t ia = pair_idx[t];
+    int k = 0, xA = 0, yA = 0, kB = 0, xB = 0, yB = 0;
+    float awA = 0.f, cwA = 0.f, awB = 0.f, cwB = 0.f;
+    const int xe = (int)(ia % (uint32_t)Nx);
+    const bool liveA = superres_pixel<TR>(ia, Nx, P, slices, weights, simslices, slice_weights, scales, psf_sums, k, xA, yA, awA, cwA);
+    const bool liveB = xe + 1 < Nx &&
+                       superres_pixel<TR>(ia + 1, Nx, P, slices, weights, simslices, slice_weights, scales, psf_sums, kB, xB, yB, awB, cwB);
+    if (!liveA && !liveB) return;
+    if (!liveA) k = kB;
+    const SliceGeom& g = geom[k];
+    PixelSetup psA = {}, psB = {};
+    if (liveA) psA = pixel_setup<TR>(g, vg, xA, yA);
+    if (liveB) psB = pixel_setup<TR>(g, vg, xB, yB);
+    const int mode = pair_mode(psA, psB, liveA, liveB);
+    if (mode == 1) {
+        bool d0 = false, d1 = false;
+        const PairWeights w = { awA, cwA, awB, cwB };
+        if (g.recur) scatter_pair<TR, true, false>(g, vg, psA, psB, liveA, liveB, w, acc2, nullptr, d0, d1);
+        else scatter_pair<TR, false, false>(g, vg, psA, psB, liveA, liveB, w, acc2, nullptr, d0, d1);
+    } else if (mode == 2) {
+        if (liveA) superres_single<TR>(g, vg, psA, awA, cwA, acc2);
+        if (liveB) superres_single<TR>(g, vg, psB, awB, cwB, acc2);
+    }
+}
+
 int svr_launch_superres_scatter(svr_context* c)
 {
     if (c->n_valid == 0) return 0;
     ProfScope prof(c, 2);
     if (c->flavor == 0)
-        superres_scatter_kernel<SvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
-            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
+        superres_scatter_kernel<SvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
+            c->n_pairs, c->pair_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
             c->geom, c->vg, c->psf_sums, c->acc2);
     else
-        superres_scatter_kernel<PvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
-            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
+        superres_scatter_kernel<PvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
+            c->n_pairs, c->pair_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
             c->geom, c->vg, c->psf_sums, c->acc2);
     SVR_KERNEL_CHECK(c);
     return 0;
