@@ -166,6 +166,23 @@ __device__ __forceinline__ void scatter_pair(const SliceGeom& g, const VolGeom& 
     const int zlo = min(czA, czB) - CEN, zhi = max(czA, czB) + HI;
     const int ylo = min(cyA, cyB) - CEN, yhi = max(cyA, cyB) + HI;
     const int xmin = min(cxA, cxB) - CEN;
+    if (MASKFLAG) {
+        // "did an accepted tap land on a masked voxel" is almost always decided by the row through the pixel's own
+        // centre voxel: test that row first, and only pixels it leaves undecided pay the 16 mask loads per row below
+        float p[SUP];
+        if (liveA) {
+            psf_row_values<TR, RECUR>(g, A.ex, A.ey, A.ez, p);
+            const int v0 = (A.cz * vy + A.cy) * vx + A.cx - CEN;
+#pragma unroll
+            for (int i = 0; i < SUP; ++i) if (p[i] != 0.0f && mask[v0 + i]) anyA = true;
+        }
+        if (liveB) {
+            psf_row_values<TR, RECUR>(g, B.ex, B.ey, B.ez, p);
+            const int v0 = (B.cz * vy + B.cy) * vx + B.cx - CEN;
+#pragma unroll
+            for (int i = 0; i < SUP; ++i) if (p[i] != 0.0f && mask[v0 + i]) anyB = true;
+        }
+    }
 #pragma unroll 1
     for (int Z = zlo; Z <= zhi; ++Z) {
         const int ozA = Z - A.cz, ozB = Z - B.cz;
@@ -188,7 +205,7 @@ __device__ __forceinline__ void scatter_pair(const SliceGeom& g, const VolGeom& 
             if (okA) {
                 const float foy = (float)oyA;
                 psf_row_values<TR, RECUR>(g, fmaf(foy, bx1, zxA), fmaf(foy, by1, zyA), fmaf(foy, bz1, zzA), p);
-                if (MASKFLAG) {
+                if (MASKFLAG && !anyA) {
                     const int v0 = rowbase + A.cx - CEN;
 #pragma unroll
                     for (int i = 0; i < SUP; ++i) if (p[i] != 0.0f && mask[v0 + i]) anyA = true;
@@ -198,7 +215,7 @@ __device__ __forceinline__ void scatter_pair(const SliceGeom& g, const VolGeom& 
             if (okB) {
                 const float foy = (float)oyB;
                 psf_row_values<TR, RECUR>(g, fmaf(foy, bx1, zxB), fmaf(foy, by1, zyB), fmaf(foy, bz1, zzB), p);
-                if (MASKFLAG) {
+                if (MASKFLAG && !anyB) {
                     const int v0 = rowbase + B.cx - CEN;
 #pragma unroll
                     for (int i = 0; i < SUP; ++i) if (p[i] != 0.0f && mask[v0 + i]) anyB = true;
@@ -228,33 +245,52 @@ __device__ __forceinline__ int pair_mode(const PixelSetup& a, const PixelSetup& 
 // K1: gaussianReconstructionKernel3D_tex (reconstruction_cuda2.cu:176-295).
 // Pass 1: sume = sum of accepted in-volume taps (mask ignored, quirk Q3); stored only if > 0.5.
 // Pass 2: scatter psf/sume * {s*scale, 1}; flag the pixel if any accepted tap landed on a masked voxel.
+// Pass 1 (one thread per valid pixel, the occupancy of the compute-bound kernels): sume; pixels that take part are
+// marked voxel_flag = 2 for pass 2 (which leaves 1 / 0 there, the flag the reference keeps).
 template <class TR>
 __global__ void __launch_bounds__(128, SVR_MINB)
-gaussian_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
-                        const float* __restrict__ slices, const float* __restrict__ scales,
-                        const SliceGeom* __restrict__ geom, VolGeom vg, const unsigned char* __restrict__ mask,
-                        float2* __restrict__ acc2, float* __restrict__ psf_sums, unsigned char* __restrict__ voxel_flag,
-                        int* __restrict__ slice_count, const char* __restrict__ spx)
+gaussian_sume_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
+                     const SliceGeom* __restrict__ geom, VolGeom vg, float* __restrict__ psf_sums,
+                     unsigned char* __restrict__ voxel_flag, const char* __restrict__ spx)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_valid) return;
     const uint32_t idx = valid_idx[t];
     const int k = idx / P, pix = idx - k * P;
     const int y = pix / Nx, x = pix - y * Nx;
-    const SliceGeom& g = geom[k];
-    const float s = slices[idx] * scales[k];
     // PVR superpixels: sume only accumulates when the pixel's own flag is '1' (patchBasedPSFReconstruction_gpu.cu:99),
     // i.e. other pixels end with sume = 0 and return; the mask is char[64*64] per patch, indexed x + 64*y.
     if (spx && spx[(size_t)k * 4096 + x + 64 * y] != '1') return;
+    const SliceGeom& g = geom[k];
     const PixelSetup ps = pixel_setup<TR>(g, vg, x, y);
-
     float sume = 0.f;
     psf_rows_dispatch<TR>(g, vg, ps, [&](int, float psf, bool, int) { sume += psf; }, [](int) {});
     if (!TR::sume_ok(sume)) return;
     psf_sums[idx] = sume;
+    voxel_flag[idx] = 2;
+}
 
-    const float inv = 1.0f / sume;
-    const float sv = s * inv;
+// Pass 2 inputs of one pixel: false when pass 1 did not mark it.
+template <class TR>
+__device__ __forceinline__ bool gaussian_pixel(uint32_t idx, int Nx, int P, const float* __restrict__ slices,
+                                               const float* __restrict__ scales, const SliceGeom* __restrict__ geom,
+                                               const VolGeom& vg, const float* __restrict__ psf_sums,
+                                               const unsigned char* __restrict__ voxel_flag, int& k, PixelSetup& ps, float& sv, float& inv)
+{
+    if (voxel_flag[idx] != 2) return false;
+    k = idx / P;
+    const int pix = idx - k * P;
+    const int y = pix / Nx, x = pix - y * Nx;
+    ps = pixel_setup<TR>(geom[k], vg, x, y);
+    inv = 1.0f / psf_sums[idx];
+    sv = slices[idx] * scales[k] * inv;
+    return true;
+}
+
+template <class TR>
+__device__ __forceinline__ bool gaussian_single(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, float sv, float inv,
+                                                const unsigned char* __restrict__ mask, float2* __restrict__ acc2)
+{
     bool any = false;
     if (ps.interior) {
         float p[TR::SUP];
@@ -272,24 +308,66 @@ gaussian_scatter_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx
             },
             [](int) {});
     }
-    if (any) {
-        voxel_flag[idx] = 1;
-        atomicAdd(&slice_count[k], 1);
+    return any;
+}
+
+// Pass 2: one thread = one pixel pair (see scatter_pair).
+template <class TR>
+__global__ void __launch_bounds__(128, SVR_MINB_PAIR)
+gaussian_scatter_kernel(uint32_t n_pairs, const uint32_t* __restrict__ pair_idx, int Nx, int P,
+                        const float* __restrict__ slices, const float* __restrict__ scales,
+                        const SliceGeom* __restrict__ geom, VolGeom vg, const unsigned char* __restrict__ mask,
+                        float2* __restrict__ acc2, const float* __restrict__ psf_sums, unsigned char* __restrict__ voxel_flag,
+                        int* __restrict__ slice_count)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    const uint32_t ia = pair_idx[t];
+    const int xe = (int)(ia % (uint32_t)Nx);
+    int k = 0, kB = 0;
+    PixelSetup psA = {}, psB = {};
+    float svA = 0.f, invA = 0.f, svB = 0.f, invB = 0.f;
+    const bool liveA = gaussian_pixel<TR>(ia, Nx, P, slices, scales, geom, vg, psf_sums, voxel_flag, k, psA, svA, invA);
+    const bool liveB = xe + 1 < Nx && gaussian_pixel<TR>(ia + 1, Nx, P, slices, scales, geom, vg, psf_sums, voxel_flag, kB, psB, svB, invB);
+    if (!liveA && !liveB) return;
+    if (!liveA) k = kB;
+    const SliceGeom& g = geom[k];
+    bool anyA = false, anyB = false;
+    const int mode = pair_mode(psA, psB, liveA, liveB);
+    if (mode == 1) {
+        const PairWeights w = { svA, invA, svB, invB };
+        if (g.recur) scatter_pair<TR, true, true>(g, vg, psA, psB, liveA, liveB, w, acc2, mask, anyA, anyB);
+        else scatter_pair<TR, false, true>(g, vg, psA, psB, liveA, liveB, w, acc2, mask, anyA, anyB);
+    } else {
+        if (liveA) anyA = gaussian_single<TR>(g, vg, psA, svA, invA, mask, acc2);
+        if (liveB) anyB = gaussian_single<TR>(g, vg, psB, svB, invB, mask, acc2);
     }
+    if (liveA) voxel_flag[ia] = anyA ? 1 : 0;
+    if (liveB) voxel_flag[ia + 1] = anyB ? 1 : 0;
+    const int n = (anyA ? 1 : 0) + (anyB ? 1 : 0);
+    if (n) atomicAdd(&slice_count[k], n);
 }
 
 int svr_launch_gaussian_scatter(svr_context* c)
 {
     if (c->n_valid == 0) return 0;
     ProfScope prof(c, 0);
-    if (c->flavor == 0)
-        gaussian_scatter_kernel<SvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
-            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2,
-            c->psf_sums, c->voxel_flag, c->slice_count, nullptr);
-    else
-        gaussian_scatter_kernel<PvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
-            c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2,
-            c->psf_sums, c->voxel_flag, c->slice_count, c->use_spx ? c->spx : nullptr);
+    const int P = c->Nx * c->Ny;
+    if (c->flavor == 0) {
+        gaussian_sume_kernel<SvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
+            c->n_valid, c->valid_idx, c->Nx, P, c->geom, c->vg, c->psf_sums, c->voxel_flag, nullptr);
+        SVR_KERNEL_CHECK(c);
+        gaussian_scatter_kernel<SvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
+            c->n_pairs, c->pair_idx, c->Nx, P, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2, c->psf_sums,
+            c->voxel_flag, c->slice_count);
+    } else {
+        gaussian_sume_kernel<PvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
+            c->n_valid, c->valid_idx, c->Nx, P, c->geom, c->vg, c->psf_sums, c->voxel_flag, c->use_spx ? c->spx : nullptr);
+        SVR_KERNEL_CHECK(c);
+        gaussian_scatter_kernel<PvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
+            c->n_pairs, c->pair_idx, c->Nx, P, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2, c->psf_sums,
+            c->voxel_flag, c->slice_count);
+    }
     SVR_KERNEL_CHECK(c);
     return 0;
 }
@@ -426,7 +504,7 @@ superres_scatter_kernel(uint32_t n_pairs, const uint32_t* __restrict__ pair_idx,
 
 int svr_launch_superres_scatter(svr_context* c)
 {
-    if (c->n_valid == 0) return 0;
+    if (c->n_pairs == 0) return 0;
     ProfScope prof(c, 2);
     if (c->flavor == 0)
         superres_scatter_kernel<SvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
