@@ -76,11 +76,11 @@ def acquisition(tmp_path_factory):
     """Oblique synthetic stacks written as NIfTI + the mask on the volume grid (stack 0 is the template: identity)."""
     from fetalreconstruction_b200.phantom import make_dataset, small_config
     d = tmp_path_factory.mktemp("acq")
-    cfg = small_config(seed=3, vol=36, n_stacks=3, slices=14, size=34, inplane=1.1, spacing=2.0)
+    cfg = small_config(seed=3, vol=48, n_stacks=3, slices=20, size=44, inplane=1.1, spacing=2.0)
     cfg.motion_mm = cfg.motion_deg = 0.0
     cfg.noise = 0.0
     cfg.corrupt_fraction = 0.0
-    cfg.mask_semi_axis = 0.25
+    cfg.mask_semi_axis = 0.36
     ds = make_dataset(cfg)
     Ny, Nx = ds.slices.shape[1:]
     names, stacks, affs = [], [], []
