@@ -52,7 +52,7 @@ def config_json(cfg, n_gpus):
                     "(BASELINE.json configs[2])",
         "step": "one outer iteration: 1 K1 + 5 K2 + 4 K3 + regulariser + EM = 10 slice-projections per slice",
         "slices": cfg.n_stacks * cfg.slices_per_stack,
-        "parallelism": f"slices sharded over {n_gpus} rank(s) (each rank a contiguous 1/N of every stack), NCCL all-reduce of "
+        "parallelism": f"slices sharded over {n_gpus} rank(s) (rank r: every N-th slice of every stack), NCCL all-reduce of "
                        "the volume accumulator",
         "l2": "inputs larger than L2: per rank the slice-side arrays are >1 GB at N=1 and the volume-side "
               "buffers 0.6 GB, all streamed every step",
@@ -246,13 +246,13 @@ def main():
 
     cfg = workload_config(args)
     S_global = cfg.n_stacks * cfg.slices_per_stack
-    # Sharding: rank r takes the r-th contiguous 1/N of the slices of EVERY stack (phantom.shard_bounds), so all ranks see
-    # the same mix of stack orientations -- the per-slice cost of the PSF kernels depends on the orientation, and whole
-    # stacks per rank left rank 0 22 % slower than rank 1 at N=2.  Global slice order = rank-major (a permutation of the
-    # acquisition order; the slice-level EM is order-independent).
-    from fetalreconstruction_b200.phantom import shard_bounds
-    per_rank = [cfg.n_stacks * (shard_bounds(cfg.slices_per_stack, r, world)[1] - shard_bounds(cfg.slices_per_stack, r, world)[0])
-                for r in range(world)]
+    # Sharding: rank r takes every N-th slice (j % N == r) of EVERY stack, so all ranks see the same mix of stack
+    # orientations and of positions along the stacks -- the per-slice cost of the PSF kernels depends on the orientation
+    # (whole stacks per rank left rank 0 22 % slower than rank 1 at N=2) and the number of valid pixels on the distance
+    # from the stack's ends (contiguous quarters of every stack: 60 % efficiency at N=4).  Global slice order = rank-major
+    # (a permutation of the acquisition order; the slice-level EM is order-independent).
+    from fetalreconstruction_b200.phantom import shard_count
+    per_rank = [cfg.n_stacks * shard_count(cfg.slices_per_stack, r, world) for r in range(world)]
     b0 = sum(per_rank[:rank]); e0 = b0 + per_rank[rank]
     ds = make_dataset(cfg, device=str(dev), shard=(rank, world))
     assert ds.S == e0 - b0

@@ -98,18 +98,19 @@ def _phantom_at(world: torch.Tensor, centres, radii, amps) -> torch.Tensor:
     return out
 
 
-def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous balanced share [lo, hi) of n items for `rank` of `world`."""
-    return rank * n // world, (rank + 1) * n // world
+def shard_count(n: int, rank: int, world: int) -> int:
+    """Number of items j in [0, n) with j % world == rank."""
+    return (n - rank + world - 1) // world if rank < n else 0
 
 
 def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: bool = True,
                  stacks: range | None = None, shard: tuple[int, int] | None = None) -> Dataset:
     """`stacks` restricts generation to a contiguous range of stacks (a rank's shard); every stack is
     seeded on its own, so the slices are identical however the stacks are sharded.
-    `shard = (rank, world)` instead gives the rank the rank-th contiguous 1/world of the slices of EVERY stack:
-    every rank then sees the same mix of orientations (the per-slice cost of the PSF kernels depends on it), so the
-    ranks are balanced by construction.  Every slice is seeded by its own (stack, index) either way."""
+    `shard = (rank, world)` instead gives the rank every world-th slice of EVERY stack (j % world == rank): every rank
+    then sees the same mix of orientations AND of positions along the stack -- the per-slice cost of the PSF kernels
+    depends on the orientation, and the number of valid pixels on how close a slice is to the end of the stack -- so
+    the ranks are balanced by construction.  Every slice is seeded by its own (stack, index) either way."""
     rng = np.random.default_rng(cfg.seed)
     vx, vy, vz = cfg.vol_size
     vol_attr = ImageAttributes(vx, vy, vz, cfg.vol_voxel, cfg.vol_voxel, cfg.vol_voxel)
@@ -135,8 +136,8 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
     Nx, Ny = cfg.slice_size
     thickness = cfg.thickness if cfg.thickness is not None else 2.0 * cfg.spacing
     stacks = range(cfg.n_stacks) if stacks is None else stacks
-    j_lo, j_hi = shard_bounds(cfg.slices_per_stack, *shard) if shard is not None else (0, cfg.slices_per_stack)
-    S = len(stacks) * (j_hi - j_lo)
+    s_rank, s_world = shard if shard is not None else (0, 1)
+    S = len(stacks) * shard_count(cfg.slices_per_stack, s_rank, s_world)
     slices = np.empty((S, Ny, Nx), np.float32)
     i2w = np.empty((S, 16), np.float32)
     w2i = np.empty((S, 16), np.float32)
@@ -170,7 +171,7 @@ def make_dataset(cfg: PhantomConfig, device: str = "cpu", perfect_registration: 
             A, Ainv = sa.image_to_world(), sa.world_to_image()
             tpar = np.concatenate([mrng.normal(0, cfg.motion_mm, 3), mrng.normal(0, cfg.motion_deg, 3)])
             corrupt = srng.uniform() < cfg.corrupt_fraction
-            if not (j_lo <= j < j_hi):                 # the random streams advance for every slice of the stack
+            if j % s_world != s_rank:                  # the random streams advance for every slice of the stack
                 continue
             T_true = rigid_matrix(*tpar)
             T_used = T_true if perfect_registration else np.eye(4)
