@@ -220,3 +220,35 @@ def test_error_reporting():
     g.InitReconstructionVolume((8, 8, 8), (1, 1, 1))
     with pytest.raises(SVRError, match="differs"):
         g.setMask((4, 4, 4), (1, 1, 1), np.ones(64, np.float32))
+
+
+# ---- the paired scatter (svr_psf.cu: scatter_pair) on the geometries that exercise each of its paths ------------------
+@pytest.mark.parametrize("size,inplane,voxel,vol,why", [
+    (35, 1.0, 1.0, 40, "odd Nx: every slice row ends in a lone pixel (partner switched off)"),
+    (20, 2.6, 1.0, 44, "pixels 2.6x coarser than the voxels: centres > 2 voxels apart in x -> one-pixel fallback"),
+    (30, 0.55, 1.0, 28, "pixels finer than the voxels: both pixels of a pair round to the same voxel (d = 0)"),
+    (36, 1.1, 1.0, 24, "volume smaller than the slices: most supports touch the volume faces (non-interior path)"),
+])
+def test_paired_scatter_paths(size, inplane, voxel, vol, why):
+    cfg = small_config(seed=17, vol=vol, n_stacks=3, slices=5, size=size, voxel=voxel, inplane=inplane, spacing=2.0)
+    ds = make_dataset(cfg)
+    res = {}
+    for name, b in (("gpu", _gpu()), ("orc", OracleReconstruction())):
+        upload_dataset(b, ds)
+        b.UpdateScaleVector(np.ones(ds.S, np.float32), np.ones(ds.S, np.float32))
+        b.InitializeEMValues()
+        vn = b.GaussianReconstruction()
+        recon0, volw, psf = b.syncCPU(), b.getVolWeights(), b.debugv_PSF_sums()
+        b.SimulateSlices()
+        sw = np.ones(ds.S, np.float32); sw[0] = 0.0; sw[2] = 0.4
+        pos = ds.slices[ds.slices > 0]
+        b.Superresolution(1, sw, False, 1.0, float(pos.min()), float(pos.max()), 150.0, 0.02 * 150.0 * 150.0)
+        res[name] = dict(vn=vn, recon0=recon0, volw=volw, psf=psf, addon=b.debugAddon(), cmap=b.debugConfidenceMap(), recon1=b.syncCPU())
+    g, o = res["gpu"], res["orc"]
+    assert np.array_equal(g["vn"], o["vn"]), why
+    check_volume(g["recon0"], o["recon0"], "K1 volume: " + why)
+    check_volume(g["volw"], o["volw"], "K1 volume weights: " + why)
+    check_pixels(g["psf"], o["psf"], "v_PSF_sums: " + why)
+    check_volume(g["addon"], o["addon"], "K3 addon: " + why, rms=1e-3, mx=8e-2)
+    check_volume(g["cmap"], o["cmap"], "K3 confidence map: " + why)
+    check_volume(g["recon1"], o["recon1"], "volume after one SR step: " + why)
