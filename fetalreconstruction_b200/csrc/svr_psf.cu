@@ -25,7 +25,7 @@
 #endif
 // The paired scatter keeps two pixel states and a 2 x 18-voxel row accumulator in registers.
 #ifndef SVR_MINB_PAIR
-#define SVR_MINB_PAIR 3
+#define SVR_MINB_PAIR 4
 #endif
 
 // ---------------------------------------------------------------------------------------------

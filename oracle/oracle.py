@@ -1,8 +1,8 @@
 """ctypes front-end of the CPU oracle (oracle/svr_oracle.c).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs.  The product package never imports this module.  Parity unpinned (see the
-header of svr_oracle.c): the reference holds no golden vectors for this path.
+--impl reference legs.  The product package never imports this module.  Pinned against the reference's
+own CUDA path (see the header of svr_oracle.c and tests/test_ref_golden.py).
 """
 from __future__ import annotations
 

@@ -5,8 +5,11 @@
  * patchBasedRobustStatistics_gpu (P6, P7), with the PVR constants of include/reconConfig.cuh and
  * include/pointSpreadFunction.cuh.
  *
- * TEST INFRASTRUCTURE ONLY (same rules as svr_oracle.c).  PARITY STATUS: "parity unpinned" -- the reference
- * holds no golden vectors for this path and cannot be built here.
+ * TEST INFRASTRUCTURE ONLY (same rules as svr_oracle.c).  PARITY STATUS: pinned against the reference's own PVR
+ * CUDA path: its unmodified patchBased*_gpu.cu / reconVolume.cu compile for sm_100a behind oracle/ref_shim/
+ * (libref_pvr.so), and every stage of one PVR iteration they produce on a B200 (tests/golden/ref_pvr_small.npz,
+ * oracle/ref_runner_pvr.py) is what tests/test_ref_golden.py holds this file to (final volume 1.2e-5 relative RMS).
+ * Not covered by the reference build: patch enumeration / extraction (IRTK host code), restated from the sources.
  *
  * Reference lines followed (paths relative to source/reconstructionGPU2/):
  *   PointSpreadFunction::sinc_pi / calcPSF / getPSFParamsPrecomp   include/pointSpreadFunction.cuh:45-116

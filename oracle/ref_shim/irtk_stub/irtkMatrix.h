@@ -1,0 +1,1 @@
+#include "irtk_stub.h"

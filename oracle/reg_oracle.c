@@ -2,9 +2,11 @@
  * reg_oracle.c -- CPU restatement of the GPU slice-to-volume registration (--useGPUReg) of
  * bkainz/fetalReconstruction: Reconstruction::registerSlicesToVolume and everything below it.
  *
- * TEST INFRASTRUCTURE ONLY (same rules as svr_oracle.c).  PARITY STATUS: "parity unpinned" -- the
- * reference holds no golden vectors for this path and cannot be built here; this file is a literal
- * restatement pinned by the known-answer tests in tests/test_reg_oracle.py.
+ * TEST INFRASTRUCTURE ONLY (same rules as svr_oracle.c).  PARITY STATUS: pinned against the reference's own
+ * CUDA path (tests/golden/ref_reg_small.npz, ref_regtrace.npz; tests/test_ref_golden.py) up to the texture
+ * unit's filter arithmetic, which a CPU cannot reproduce (deviation D6 below: similarities within 2e-3; the
+ * CUDA path samples through the texture unit and agrees to 1.5e-6), and by the known-answer tests in
+ * tests/test_reg_oracle.py.
  *
  * Reference lines followed (paths relative to source/reconstructionGPU2/, cuda2.cu = reconstruction_cuda2.cu):
  *   generateGaussianKernel / GaussX/YKernel / FilterGaussStack    GPUGauss/gaussfilter.cu:56-277

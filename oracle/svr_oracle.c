@@ -6,11 +6,12 @@
  * and bench.py's cpu_baseline / --impl reference legs use it, and only as the checker
  * or as the timed CPU arm.
  *
- * PARITY STATUS: "parity unpinned".  The reference ships no golden vectors, no tests and
- * no expected outputs for this path, and its CUDA sources cannot be
- * built with CUDA 12 (legacy texture references, sm_30 targets, Boost/TBB/GSL absent).
- * This file is therefore a line-by-line restatement of the reference kernels, pinned only
- * by analytic known-answer tests in tests/test_oracle_known_answers.py.
+ * PARITY STATUS: pinned against the reference's own CUDA path.  The reference ships no golden
+ * vectors, tests or expected outputs for this path; its CUDA sources do
+ * compile for sm_100a behind the shim headers of oracle/ref_shim/ (oracle/Makefile, `make ref`),
+ * and their outputs on a B200 (tests/golden/ref_{steps,svr}_small.npz, oracle/ref_runner.py) are what
+ * tests/test_ref_golden.py holds this line-by-line restatement to, stage by stage; the analytic
+ * known-answer tests of tests/test_oracle_known_answers.py pin the mathematics.
  *
  * Every function cites the reference file:line it follows; paths are relative to
  * /root/reference/source/reconstructionGPU2/ ("cuda2.cu" = reconstruction_cuda2.cu,

@@ -3,7 +3,8 @@
 
 STATUS: the reference (bkainz/fetalReconstruction) ships no golden vectors, tests or expected outputs for this
 path and cannot be built here, so these vectors pin the ORACLE against regressions and give
-the CUDA path a fixed target; they do not pin the oracle against the reference ("parity unpinned").
+the CUDA path a fixed target; the vectors that pin both against the reference itself are ref_*.npz (written by
+oracle/ref_runner.py / ref_runner_pvr.py from the reference's own CUDA code on a B200; tests/test_ref_golden.py).
 
     python tests/golden/make_golden.py        # rewrites the fixtures (deterministic)
 """

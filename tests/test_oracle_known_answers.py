@@ -1,7 +1,7 @@
 """CPU: pins the oracle (oracle/svr_oracle.c) with analytic known answers.
 
 The reference has no golden vectors, tests or expected outputs for this path, so the
-oracle is "parity unpinned" with respect to the reference; these tests pin it against mathematics the
+oracle is pinned against the reference's own CUDA outputs in tests/test_ref_golden.py; these tests pin it against mathematics the
 reference's formulas imply (cited per test).
 """
 import math

@@ -1,6 +1,7 @@
 """CPU: the PVR oracle (oracle/pvr_oracle.c) against analytic known answers, the patch enumeration, the pure-host
 patch-level EM of the C ABI against the oracle, and the PVR pipeline on the oracle twin.
-The reference holds no golden vectors for this path (parity unpinned)."""
+The reference holds no golden vectors for this path; the vectors its own PVR CUDA code produces are pinned in
+tests/test_ref_golden.py."""
 import ctypes as C
 
 import numpy as np

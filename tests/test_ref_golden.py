@@ -136,3 +136,43 @@ def test_cuda_matches_reference_registration():
     pg = np.stack([rigid_parameters(m.reshape(4, 4).astype(np.float64)) for m in one])
     pr = np.stack([rigid_parameters(m.reshape(4, 4).astype(np.float64)) for m in trace["T_111"]])
     assert np.abs(pg - pr).max() <= 1e-3, np.abs(pg - pr).max()
+
+
+# ---- PVR: the reference's patch-based CUDA path (oracle/_ref/libref_pvr.so, oracle/ref_runner_pvr.py) -------------
+# tests/golden/ref_pvr_small.npz = every stage of one PVR iteration (PSF reconstruction, equalize, simulate, robust
+# statistics init, E-step, 2 x {scale, super-resolution, regularise, simulate, M-step, E-step}) written by the UNMODIFIED
+# patchBased*_gpu.cu / reconVolume.cu of the reference on a B200, on the patch list and patch values of our enumeration.
+PVR_FIELDS = ["p1_recon_raw", "p1_volw", "p1_psf_sums", "p1_recon", "p2_sim", "p2_simw", "e0_weights", "r0_recon", "r0_sim",
+              "r0_weights", "r1_recon", "r1_sim", "r1_weights", "volume"]
+PVR_SCALARS = ["rs_init", "e0_patch_scale", "e0_patch_weight", "e0_state", "r0_patch_scale", "r0_mstep", "r0_patch_weight",
+               "r1_patch_scale", "r1_mstep", "r1_patch_weight"]
+PVR_MASKED = ["r0_addon", "r0_cmap", "r1_addon", "r1_cmap"]     # compared inside the mask: the CUDA path applies the per-tap
+                                                                # mask test once per voxel afterwards
+
+
+def _check_pvr(got, ref):
+    from oracle.ref_runner_pvr import REF_PVR_CASE
+    from pvr_case import make_pvr_case
+    assert np.array_equal(got["per_stack"], ref["per_stack"])
+    assert np.array_equal(got["patches"], ref["patches"])
+    assert np.array_equal(np.asarray(got["p2_inside"]).astype(np.int8), np.asarray(ref["p2_inside"]).astype(np.int8))
+    _check(got, ref, PVR_FIELDS, FIELD)
+    _check(got, ref, PVR_SCALARS, SCALAR)
+    inside = make_pvr_case(**REF_PVR_CASE)["mask"].ravel() != 0
+    for k in PVR_MASKED:
+        m, r = rel_stats(np.asarray(got[k], np.float64)[inside], np.asarray(ref[k], np.float64)[inside])
+        assert r <= FIELD[0] and m <= FIELD[1], f"{k}: rms/max = {(r, m)}"
+
+
+def test_oracle_matches_reference_pvr():
+    from fetalreconstruction_b200.pvr import PVRPipeline
+    from oracle.oracle_backend_pvr import OraclePatchReconstruction
+    from oracle.ref_runner_pvr import pvr_stages
+    _check_pvr(pvr_stages(OraclePatchReconstruction(), PVRPipeline), _ref("pvr"))
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_pvr():
+    from fetalreconstruction_b200.pvr import PatchReconstruction, PVRPipeline
+    from oracle.ref_runner_pvr import pvr_stages
+    _check_pvr(pvr_stages(PatchReconstruction(0), PVRPipeline), _ref("pvr"))

@@ -1,7 +1,8 @@
 """CPU: the registration oracle (oracle/reg_oracle.c) against analytic known answers, and the host
 front-end (fetalreconstruction_b200/registration.py) against properties of irtkResamplingWithPadding.
 
-The reference holds no golden vectors for this path (parity unpinned); these tests pin the restatement.
+The reference holds no golden vectors for this path (its own outputs are pinned in tests/test_ref_golden.py); these
+tests pin the restatement against known answers.
 """
 import numpy as np
 import pytest
