@@ -17,11 +17,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 REF_PVR_CASE = dict(seed=41, vol=32, n_stacks=2, slices=4, size=32, pbb=(16, 16), stride=(8, 8))   # volume size a multiple of 8
 
 
-def pvr_stages(backend, pipeline_cls, patch_cube=None, rec_iterations=2):
+def pvr_stages(backend, pipeline_cls, patch_cube=None, rec_iterations=2, case=None):
     """One PVR iteration (irtkPatchBasedReconstruction.cpp:482-560) with every stage output captured."""
     from fetalreconstruction_b200.pvr import PVRParams
     from pvr_case import make_pvr_case, setup_backend
-    case = make_pvr_case(**REF_PVR_CASE)
+    case = case or make_pvr_case(**REF_PVR_CASE)
     ds = case["ds"]
     if patch_cube is None:
         b = setup_backend(backend, case)
