@@ -292,6 +292,14 @@ def main():
         launches = backend.launch_count - launches0
         prof = backend.profile_read()
 
+        # every rank must hold the same volume replica after a step (the accumulators were all-reduced, the rest is redundant)
+        chk = torch.tensor([float(np.abs(backend.syncCPU().astype(np.float64)).sum())], dtype=torch.float64, device=dev)
+        chk_lo, chk_hi = chk.clone(), chk.clone()
+        if world > 1:
+            dist.all_reduce(chk_lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(chk_hi, op=dist.ReduceOp.MAX)
+        replicas_identical = bool(chk_lo.item() == chk_hi.item()) and bool(np.isfinite(chk.item()))
+
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         ln = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -407,7 +415,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_json(cfg, world),
                 "volumes_per_hour": vph, "roofline": roofline, "cpu_baseline": base, "reference_cuda": ref_cuda, "e2e": e2e,
-                "registration": registration, "gpu_launches": int(ln.item()), "clocks": clocks}
+                "registration": registration, "gpu_launches": int(ln.item()), "clocks": clocks,
+                "replicas_identical": replicas_identical}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -91,6 +91,8 @@ _SIGNATURES = {
     "pvr_set_psf": (ip, [vp, vp, vp, fp]),
     "pvr_init_patch_based_recon": (ip, [vp, ip, vp, ip, ip, ip, vp]),
     "pvr_psf_reconstruction": (ip, [vp]),
+    "pvr_psf_reconstruction_local": (ip, [vp]),
+    "pvr_psf_reconstruction_finish": (ip, [vp]),
     "pvr_simulate_patches": (ip, [vp]),
     "pvr_superresolution_run": (ip, [vp]),
     "pvr_superresolution_regularize": (ip, [vp, ip, fp, fp, fp, fp, fp]),

@@ -242,6 +242,22 @@ int pvr_psf_reconstruction(svr_context* c)
     return sync_(c);
 }
 
+// Split-phase P1 for N ranks (one process per GPU, patches sharded): scatter this rank's patches into the interleaved
+// accumulator, let the host all-reduce svr_device_buffer(SVR_BUF_ACCUMULATOR) over the ranks, then unpack it.
+int pvr_psf_reconstruction_local(svr_context* c)
+{
+    if (int r = pvr_ready(c, "pvr_psf_reconstruction_local")) return r;
+    if (svr_launch_gaussian_scatter(c)) return 1;
+    return sync_(c);
+}
+
+int pvr_psf_reconstruction_finish(svr_context* c)
+{
+    if (int r = pvr_ready(c, "pvr_psf_reconstruction_finish")) return r;
+    if (svr_launch_unpack_acc(c)) return 1;
+    return sync_(c);
+}
+
 int pvr_simulate_patches(svr_context* c)
 {
     if (int r = pvr_ready(c, "pvr_simulate_patches")) return r;

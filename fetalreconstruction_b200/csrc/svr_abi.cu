@@ -376,6 +376,8 @@ int svr_gaussian_reconstruction_local(svr_context* c)
     }
     SVR_CUDA(c, cudaMemsetAsync(c->acc2, 0, c->V * sizeof(float2), c->stream));
     if (svr_launch_gaussian_scatter(c)) return 1;
+    // the caller all-reduces the accumulator next, possibly on another stream: like every entry point, return when done
+    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -487,7 +489,9 @@ int svr_superresolution_local(svr_context* c, const float* slice_weight)
     if (int r = ready(c, "svr_superresolution")) return r;
     if (slice_weight && c->S) if (int r = svr_update_slice_weights(c, slice_weight)) return r;
     SVR_CUDA(c, cudaMemsetAsync(c->acc2, 0, c->V * sizeof(float2), c->stream));
-    return svr_launch_superres_scatter(c);
+    if (svr_launch_superres_scatter(c)) return 1;
+    SVR_CUDA(c, cudaStreamSynchronize(c->stream));      // see svr_gaussian_reconstruction_local
+    return 0;
 }
 
 int svr_superresolution_finish(svr_context* c, int adaptive, float alpha, float min_i, float max_i, float delta, float lambda)

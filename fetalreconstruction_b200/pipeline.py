@@ -76,8 +76,14 @@ class Comm:
         return self._reduce_np(arr, self.dist.ReduceOp.MAX) if self.active else arr
 
     def sum_device(self, tensor):
+        """In-place all-reduce of a device buffer of the library.  The collective is ordered on torch's current stream;
+        the library may run on a stream of its own (svr_set_stream not called), so the host waits for the result before
+        the next library call can touch the buffer (a few microseconds when the streams are the same)."""
         if self.active:
             self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
+            if tensor.is_cuda:
+                import torch
+                torch.cuda.current_stream(tensor.device).synchronize()
 
     def barrier(self):
         if self.active:

@@ -123,6 +123,27 @@ class PatchReconstruction:
     # hot path
     def patchBasedPSFReconstruction_gpu(self): self._ck(self._lib.pvr_psf_reconstruction(self._h))
     def patchBasedSimulatePatches_gpu(self): self._ck(self._lib.pvr_simulate_patches(self._h))
+
+    # N ranks: split phases around the all-reduce of the accumulator (include/pvr_abi.h)
+    def psf_reconstruction_local(self): self._ck(self._lib.pvr_psf_reconstruction_local(self._h))
+    def psf_reconstruction_finish(self): self._ck(self._lib.pvr_psf_reconstruction_finish(self._h))
+
+    def accumulators(self, phase):
+        """Device buffers the ranks must sum after `phase` ("psf" or "superresolution"): the interleaved accumulator."""
+        from .reconstruction import _DeviceArray
+        ptr, nb = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.svr_device_buffer(self._h, 0, C.byref(ptr), C.byref(nb)))
+        return [_DeviceArray(ptr.value, nb.value // 4, self)]
+
+    def rs_initialize_robust_statistics_local(self):
+        s2 = (C.c_double * 2)()
+        self._ck(self._lib.svr_initialize_robust_statistics_local(self._h, s2))
+        return np.array([s2[0], s2[1]], np.float64)
+
+    def rs_mstep_local(self):
+        s5 = (C.c_double * 5)()
+        self._ck(self._lib.svr_mstep_local(self._h, s5))
+        return np.array(list(s5), np.float64)
     def superresolution_run(self): self._ck(self._lib.pvr_superresolution_run(self._h))
 
     def superresolution_regularize(self, adaptive, alpha, min_intensity, max_intensity, delta, lambda_):
@@ -206,8 +227,16 @@ class PVRParams:
 class PVRPipeline:
     """irtkPatchBasedReconstruction<T>::run() from the first iteration on, registration excluded."""
 
-    def __init__(self, backend, min_intensity, max_intensity, params: PVRParams | None = None):
+    def __init__(self, backend, min_intensity, max_intensity, params: PVRParams | None = None, comm=None, global_index=None,
+                 patches_per_stack_global=None):
+        """N ranks (one process per GPU): `backend` holds this rank's patches, `global_index[i]` is the position of its
+        i-th patch in the stack-major order of ALL patches and `patches_per_stack_global` their count per stack; the
+        ranks exchange the volume accumulators (all-reduce after P1 and P3), the partial sums of the robust statistics and
+        the per-patch vectors, and every rank runs the identical patch-level EM."""
         self.b = backend
+        self.comm = comm
+        self.gidx = None if global_index is None else np.asarray(global_index, np.int64)
+        self.pps_global = patches_per_stack_global
         self.p = params or PVRParams()
         self.min_intensity, self.max_intensity = float(min_intensity), float(max_intensity)
         self.alpha = (0.05 / self.p.lambda_) * self.p.delta * self.p.delta
@@ -215,9 +244,31 @@ class PVRPipeline:
         self.sigma_s, self.mix_s, self.mean_s, self.mean_s2, self.sigma_s2 = 0.025, 0.9, 0.0, 0.0, 0.0
         self.patch_potential = None
 
+    @property
+    def distributed(self):
+        return self.comm is not None and self.comm.active
+
+    def _allreduce(self, phase):
+        for buf in self.b.accumulators(phase):
+            if isinstance(buf, np.ndarray):
+                buf[...] = self.comm.sum(buf)                     # CPU twin (gloo)
+            else:
+                import torch
+                self.comm.sum_device(torch.as_tensor(buf, device=self.comm.device))
+
+    def _gather(self, local):
+        """Per-patch vector of this rank -> the global stack-major vector (zero-filled all-reduce)."""
+        g = np.zeros(int(np.sum(self.pps_global)), np.float64)
+        g[self.gidx] = local
+        return self.comm.sum(g).astype(np.float32)
+
     # patchBasedRobustStatistics_gpu<T>
     def InitializeRobustStatistics(self):
-        self.sigma = self.b.rs_InitializeRobustStatistics()
+        if self.distributed:
+            s2 = self.comm.sum(self.b.rs_initialize_robust_statistics_local())
+            self.sigma = float(np.float32(s2[0]) / np.float32(s2[1]))
+        else:
+            self.sigma = self.b.rs_InitializeRobustStatistics()
         self.sigma_s, self.mix, self.mix_s = 0.025, 0.9, 0.9
         self.m = float(np.float32(1.0) / (np.float32(2.1) * np.float32(self.max_intensity)
                                           - np.float32(1.9) * np.float32(self.min_intensity)))
@@ -227,12 +278,23 @@ class PVRPipeline:
         scales, weights = self.b.rs_get_scales_weights()
         weights = weights.astype(np.float32).copy()
         state = np.array([self.sigma_s, self.mix_s, self.mean_s, self.mean_s2, self.sigma_s2], np.float32)
-        self.patch_potential = host_patch_em(self.b.patches_per_stack, pot, scales, weights, self.p.step, state)
+        if self.distributed:
+            g_pot, g_sc, g_w = self._gather(pot), self._gather(scales), np.ascontiguousarray(self._gather(weights), np.float32)
+            self.patch_potential = host_patch_em(self.pps_global, g_pot, g_sc, g_w, self.p.step, state)
+            weights = np.ascontiguousarray(g_w[self.gidx], np.float32)
+        else:
+            self.patch_potential = host_patch_em(self.b.patches_per_stack, pot, scales, weights, self.p.step, state)
         self.sigma_s, self.mix_s, self.mean_s, self.mean_s2, self.sigma_s2 = (float(v) for v in state)
         self.b.rs_set_scales_weights(scales, weights)
 
     def MStep(self, it):
-        self.sigma, self.mix, self.m = self.b.rs_MStep(it, self.p.step, self.sigma, self.mix, self.m)
+        if self.distributed:
+            from .reconstruction import mstep_finish
+            s5 = self.b.rs_mstep_local()
+            sums = self.comm.sum(s5[:3].copy()); mn = self.comm.min(s5[3:4].copy()); mx = self.comm.max(s5[4:5].copy())
+            self.sigma, self.mix, self.m = mstep_finish(np.concatenate([sums, mn, mx]), it, self.p.step, self.sigma, self.mix, self.m)
+        else:
+            self.sigma, self.mix, self.m = self.b.rs_MStep(it, self.p.step, self.sigma, self.mix, self.m)
 
     def Scale(self):
         return self.b.rs_Scale()
@@ -241,7 +303,12 @@ class PVRPipeline:
         b, p = self.b, self.p
         b.rs_initializeEMValues()
         b.recon_reset()
-        b.patchBasedPSFReconstruction_gpu()
+        if self.distributed:
+            b.psf_reconstruction_local()
+            self._allreduce("psf")
+            b.psf_reconstruction_finish()
+        else:
+            b.patchBasedPSFReconstruction_gpu()
         b.recon_equalize()
         b.patchBasedSimulatePatches_gpu()
         self.InitializeRobustStatistics()
@@ -250,6 +317,8 @@ class PVRPipeline:
             self.Scale()
             b.recon_resetAddonCmap()
             b.superresolution_run()
+            if self.distributed:
+                self._allreduce("superresolution")
             b.superresolution_regularize(p.adaptive, self.alpha, self.min_intensity, self.max_intensity, p.delta, p.lambda_)
             b.patchBasedSimulatePatches_gpu()
             self.MStep(i + 1)

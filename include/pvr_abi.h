@@ -68,6 +68,12 @@ int pvr_init_patch_based_recon(svr_context *ctx, int stack, const float *stack_d
 /* ---- the hot path (every call covers all stacks) ---------------------------------------------------- */
 /* ref: patchBasedPSFReconstruction_gpu patchBasedPSFReconstruction_gpu.cu:41-160 (P1); accumulates into the volume */
 int pvr_psf_reconstruction(svr_context *ctx);
+/* Multi-GPU (one process per GPU, patches sharded over the ranks; the reference is single-device here): P1 in two
+ * phases around the host's all-reduce of svr_device_buffer(ctx, SVR_BUF_ACCUMULATOR, ...); P3 needs no extra entry point
+ * (all-reduce the same buffer between pvr_superresolution_run and pvr_superresolution_regularize); the robust-statistics
+ * partial sums come from svr_initialize_robust_statistics_local / svr_mstep_local + svr_mstep_finish (same context type). */
+int pvr_psf_reconstruction_local(svr_context *ctx);
+int pvr_psf_reconstruction_finish(svr_context *ctx);
 /* ref: patchBasedSimulatePatches_gpu patchBasedSimulatePatches_gpu.cu:41-146 (P2) incl. updateReconTex */
 int pvr_simulate_patches(svr_context *ctx);
 /* ref: patchBasedSuperresolution_gpu<T>::run patchBasedSuperresolution_gpu.cu:34-144 (P3); accumulates into addon / cmap */

@@ -113,6 +113,24 @@ class OraclePatchReconstruction:
         orc.lib().pvr_psf_reconstruction(C.byref(g.c), _ptr(self.patches), _ptr(self.scales), _ptr(self.mask), self._spx_ptr(),
                                          _ptr(self.recon), _ptr(self.volw), _ptr(self.psf_sums))
 
+    # N ranks (PVRPipeline with a Comm): the twin keeps {recon, volw} / {addon, cmap} as separate arrays
+    def psf_reconstruction_local(self): self.patchBasedPSFReconstruction_gpu()
+    def psf_reconstruction_finish(self): pass
+    def accumulators(self, phase): return [self.recon, self.volw] if phase == "psf" else [self.addon, self.cmap]
+
+    def rs_initialize_robust_statistics_local(self):
+        sa, sb = C.c_double(), C.c_double()
+        f = orc.lib().pvr_initialize_robust_statistics
+        f.restype = C.c_float
+        f(C.c_size_t(self.NP), _ptr(self.patches), _ptr(self.siminside), _ptr(self.simpatches), _ptr(self.simweights), C.byref(sa), C.byref(sb))
+        return np.array([sa.value, sb.value], np.float64)
+
+    def rs_mstep_local(self):
+        s5 = np.zeros(5, np.float64)
+        orc.lib().pvr_mstep_sums(self.n, self.pbx, self.pby, _ptr(self.patches), _ptr(self.weights), _ptr(self.simpatches),
+                                 _ptr(self.simweights), _ptr(self.scales), _ptr(s5))
+        return s5
+
     def patchBasedSimulatePatches_gpu(self):
         g = self._geom()
         orc.lib().pvr_simulate_patches(C.byref(g.c), _ptr(self.patches), _ptr(self.psf_sums), _ptr(self.recon), _ptr(self.mask),

@@ -58,3 +58,22 @@ def setup_backend(b, case, device_patch_init=True, spx=None):
     else:
         b.patches_copyFromHost(case["cube"])
     return b
+
+
+def shard_case(case, rank, world):
+    """The rank's share of a PVR case: every world-th patch of every stack (balanced by construction, as bench.py shards
+    slices).  Returns (sub-case, global_index of its patches in the stack-major order of all patches)."""
+    idx, per_stack, o = [], [], 0
+    for n in case["per_stack"]:
+        mine = [o + j for j in range(n) if j % world == rank]
+        idx += mine
+        per_stack.append(len(mine))
+        o += n
+    idx = np.asarray(idx, np.int64)
+    sub = dict(case)
+    sub["per_stack"] = per_stack
+    sub["attrs"] = [case["attrs"][i] for i in idx]
+    sub["trans"] = [case["trans"][i] for i in idx]
+    for k in ("cube", "i2w", "w2i", "T", "Tinv"):
+        sub[k] = np.ascontiguousarray(case[k][idx])
+    return sub, idx
