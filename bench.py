@@ -179,14 +179,15 @@ def run_reference_cuda(cfg, stacks=1):
     tool = os.path.join(ROOT, "tools", "ref_bench.py")
     try:
         subprocess.run([sys.executable, tool, "gen", "--stacks", str(stacks)], check=True, capture_output=True, text=True, timeout=300)
-        r = subprocess.run([sys.executable, tool, "ref", "--rec-iters", "4"], check=True, capture_output=True, text=True, timeout=600)
+        r = subprocess.run([sys.executable, tool, "ref", "--rec-iters", "4", "--timing-only"], check=True, capture_output=True, text=True,
+                           timeout=600)
         line = [l for l in r.stdout.splitlines() if l.startswith("REFBENCH_JSON ")][-1]
         d = json.loads(line[len("REFBENCH_JSON "):])
     except Exception as e:                                   # the baseline is optional; the bench line is not
         return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
     return {"value": d["S"] * PROJ_PER_SLICE_STEP / d["iteration_s"], "unit": UNIT, "kind": "reference CUDA path on this GPU",
-            "sample": f"{d['S']} slices ({stacks} stack(s) of the C3 workload, full 256^3 volume), one outer iteration, "
-                      f"{d['iteration_s']:.3f} s wall; every call synchronous as in the reference",
+            "sample": f"{d['S']} slices ({stacks} stack(s) of the C3 workload, full 256^3 volume), one outer iteration after one untimed "
+                      f"warm-up iteration, {d['iteration_s']:.3f} s wall; every call synchronous as in the reference",
             "ms_per_call": {k: round(v, 3) for k, v in d["ms_per_call"].items() if v >= 0.05}}
 
 
