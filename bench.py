@@ -336,6 +336,7 @@ def main():
         if not args.no_e2e:
             pinned = torch.from_numpy(ds.slices).pin_memory()
             cube = pinned.numpy()
+            vol_host = torch.empty(backend.V, dtype=torch.float32).pin_memory().numpy()       # the caller's (pinned) output buffer
             h2d = d2h = 0
             comm.barrier()
             torch.cuda.synchronize()
@@ -348,10 +349,10 @@ def main():
                 backend.SetSliceMatrices(ds.trans, ds.trans_inv, ds.i2w, ds.w2i, ds.i2w, ds.w2i, ds.recon_i2w, ds.recon_w2i)
                 h2d += 4 * ds.trans.nbytes
                 pipe2.outer_iteration(it)
-                vol = backend.syncCPU()                       # image<iter>_GPU.nii.gz (reconstruction.cc:1189-1193)
+                vol = backend.syncCPU(out=vol_host)           # image<iter>_GPU.nii.gz (reconstruction.cc:1189-1193)
                 d2h += vol.nbytes
             pipe2.ScaleVolumeGPU()
-            vol = backend.syncCPU()
+            vol = backend.syncCPU(out=vol_host)
             d2h += vol.nbytes
             comm.barrier()
             torch.cuda.synchronize()

@@ -260,8 +260,12 @@ class Reconstruction:
         return out[:self.regW * self.regH * self.regS].reshape(self.regS, self.regH, self.regW)
 
     # -- downloads ------------------------------------------------------------------------------
-    def syncCPU(self):
-        out = np.empty(self.V, np.float32)
+    def syncCPU(self, out=None):
+        """Volume -> host.  `out` may be a caller-owned float32 buffer of V elements (e.g. pinned memory: the copy then runs
+        at PCIe speed instead of through the driver's staging buffer)."""
+        if out is None:
+            out = np.empty(self.V, np.float32)
+        assert out.dtype == np.float32 and out.size >= self.V and out.flags["C_CONTIGUOUS"]
         self._ck(self._lib.svr_sync_cpu(self._h, _p(out)))
         return out
 
