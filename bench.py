@@ -167,7 +167,10 @@ def run_cpu_baseline(cfg, steps=1, warmup=0):
     return {"value": ds.S * PROJ_PER_SLICE_STEP / t, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
             "sample": f"{ds.S} mid-stack slices (1 axis-aligned + 1 oblique stack) of the {cfg.name} workload, full "
                       f"{cfg.vol_size[0]}^3 volume, one outer iteration (10 slice-projections per slice), "
-                      f"{t:.1f} s per step; oracle/svr_oracle.c with OpenMP"}, t
+                      f"{t:.1f} s per step; oracle/svr_oracle.c with OpenMP.  NB this port runs the reference's CUDA algorithm (4096 PSF taps per "
+                      "pixel and projection) on the CPU; the reference's IRTK/TBB CPU path, which cannot be built here, precomputes a "
+                      "sparse slice-to-volume matrix per outer iteration (CoeffInit, irtkReconstructionGPU.cc:2305-2673, a few dozen "
+                      "coefficients per pixel) and is expected to be one to two orders of magnitude faster than this figure"}, t
 
 
 def run_reference_cuda(cfg, stacks=1):
