@@ -12,7 +12,7 @@ the interleaved accumulator is all-reduced with NCCL after K1 and after every K3
   python bench.py --gpus 1 --steps 3 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
          bench.py --gpus 8 --steps 3 --warmup 3
-  python bench.py --impl reference ...      # the CPU arm (oracle port of the reference's algorithm)
+  python bench.py --impl reference ...      # the CPU arm (restatement of the reference's --useCPU path, oracle/cpu_path.c)
 """
 from __future__ import annotations
 
@@ -131,30 +131,58 @@ def recorded_traffic():
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_sample_dataset(cfg):
-    """A bounded sample of the same workload for the CPU arm: 2 mid-stack slices (one axis-aligned stack,
-    one oblique stack) against the full-size volume and mask."""
+def cpu_sample_dataset(cfg, per_stack=8):
+    """A bounded sample of the same workload for the CPU arm: `per_stack` mid-stack slices of one axis-aligned and one
+    oblique stack against the full-size volume and mask."""
     from fetalreconstruction_b200.phantom import make_dataset
     st = [0, min(4, cfg.n_stacks - 1)]
     ds = make_dataset(cfg, device="cpu", stacks=st)
-    mid = cfg.slices_per_stack // 2
-    keep = np.array([mid, cfg.slices_per_stack + mid])
+    per_stack = min(per_stack, cfg.slices_per_stack)
+    lo = (cfg.slices_per_stack - per_stack) // 2
+    keep = np.concatenate([np.arange(lo, lo + per_stack), cfg.slices_per_stack + np.arange(lo, lo + per_stack)])
     for name in ("slices", "i2w", "w2i", "trans", "trans_inv", "dims", "stack_index"):
         setattr(ds, name, np.ascontiguousarray(getattr(ds, name)[keep]))
     return ds
 
 
+class _Timed:
+    """Sums the wall time of a backend's method calls by name."""
+
+    def __init__(self, b):
+        object.__setattr__(self, "_b", b)
+        object.__setattr__(self, "times", {})
+
+    def __getattr__(self, name):
+        a = getattr(self._b, name)
+        if not callable(a):
+            return a
+
+        def f(*args, **kw):
+            t = time.perf_counter()
+            r = a(*args, **kw)
+            self.times[name] = self.times.get(name, 0.0) + time.perf_counter() - t
+            return r
+        return f
+
+    def __setattr__(self, k, v):
+        setattr(self._b, k, v)
+
+
 def cpu_step(ds):
-    """One outer iteration (the same 10 slice-projections per slice) on the oracle port."""
+    """One outer iteration (the same 10 slice-projections per slice) of the reference's CPU path as restated in
+    oracle/cpu_path.c + cpu_backend.py: CoeffInit, Gaussian reconstruction, 5 SimulateSlices, 4 Superresolution, EM."""
     from fetalreconstruction_b200.pipeline import SVRPipeline, SVRParams, upload_dataset
-    from oracle.oracle_backend import OracleReconstruction
-    b = OracleReconstruction()
+    from oracle.cpu_backend import CpuPathReconstruction
+    b = _Timed(CpuPathReconstruction())
     upload_dataset(b, ds)
     p = SVRPipeline(b, ds.S, 0, ds.S, params=SVRParams())
     p.InitializeEMGPU(ds.slices)
+    b.times.clear()
     t0 = time.perf_counter()
     p.outer_iteration(0)
-    return time.perf_counter() - t0
+    total = time.perf_counter() - t0
+    volume_side = sum(b.times.get(k, 0.0) for k in ("superresolution_finish", "gaussian_reconstruction_finish", "maskVolume"))
+    return total, volume_side
 
 
 def run_cpu_baseline(cfg, steps=1, warmup=0):
@@ -162,15 +190,20 @@ def run_cpu_baseline(cfg, steps=1, warmup=0):
     ds = cpu_sample_dataset(cfg)
     for _ in range(warmup):
         cpu_step(ds)
-    times = [cpu_step(ds) for _ in range(max(steps, 1))]
-    t = float(np.mean(times))
+    runs = [cpu_step(ds) for _ in range(max(steps, 1))]
+    t = float(np.mean([r[0] for r in runs]))
+    tv = float(np.mean([r[1] for r in runs]))
+    S_full = cfg.n_stacks * cfg.slices_per_stack
+    t_full = tv + (t - tv) * S_full / ds.S               # volume-side work (regulariser, masking) does not grow with the slices
     return {"value": ds.S * PROJ_PER_SLICE_STEP / t, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-            "sample": f"{ds.S} mid-stack slices (1 axis-aligned + 1 oblique stack) of the {cfg.name} workload, full "
-                      f"{cfg.vol_size[0]}^3 volume, one outer iteration (10 slice-projections per slice), "
-                      f"{t:.1f} s per step; oracle/svr_oracle.c with OpenMP.  NB this port runs the reference's CUDA algorithm (4096 PSF taps per "
-                      "pixel and projection) on the CPU; the reference's IRTK/TBB CPU path, which cannot be built here, precomputes a "
-                      "sparse slice-to-volume matrix per outer iteration (CoeffInit, irtkReconstructionGPU.cc:2305-2673, a few dozen "
-                      "coefficients per pixel) and is expected to be one to two orders of magnitude faster than this figure"}, t
+            "sample": f"{ds.S} mid-stack slices (8 of an axis-aligned + 8 of an oblique stack) of the {cfg.name} workload, full "
+                      f"{cfg.vol_size[0]}^3 volume, one outer iteration (10 slice-projections per slice), {t:.1f} s per step, of which "
+                      f"{tv:.1f} s volume-side (regulariser) that does not grow with the number of slices.  The port is the reference's "
+                      "CPU (--useCPU) formulation -- sparse slice-to-volume matrix of CoeffInit (Gaussian PSF, trilinear splat, "
+                      "irtkReconstructionGPU.cc:2305-2673) + the functors applying it, OpenMP where the reference uses TBB "
+                      "(oracle/cpu_path.c); its IRTK/TBB original cannot be built here",
+            "extrapolated_full_workload": {"value": S_full * PROJ_PER_SLICE_STEP / t_full, "unit": UNIT,
+                                           "how": f"volume-side time + slice-side time x {S_full}/{ds.S}"}}, t
 
 
 def run_reference_cuda(cfg, stacks=1):
@@ -206,9 +239,9 @@ def run_reference(args):
             "config": config_json(cfg, args.gpus), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference's IRTK/TBB CPU path cannot be compiled here (Boost/TBB/GSL absent, SURVEY.md 8c): this arm "
-                    "times the oracle port of its algorithm on the host cores; warm-up capped at 1 step (deterministic CPU "
-                    "code).  The reference's own CUDA path does compile (oracle/_ref) and is reported by the main arm as "
-                    "`reference_cuda`."}
+                    "times our restatement of that path (oracle/cpu_path.c: CoeffInit's sparse matrix + the functors applying "
+                    "it) on the host cores; warm-up capped at 1 step (deterministic CPU code).  The reference's own CUDA path "
+                    "does compile (oracle/_ref) and is reported by the main arm as `reference_cuda`."}
     print(json.dumps(line))
 
 

@@ -39,7 +39,7 @@ class _Geom(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("svr_oracle.c", "reg_oracle.c", "pvr_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("svr_oracle.c", "reg_oracle.c", "pvr_oracle.c", "cpu_path.c", "Makefile")]
     newest = max(os.path.getmtime(f) for f in srcs if os.path.exists(f))
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.run(["make", "-C", _HERE, "clean", "all"], check=True, capture_output=True)

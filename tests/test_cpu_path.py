@@ -1,0 +1,59 @@
+"""CPU: the restatement of the reference's CPU (--useCPU) projections (oracle/cpu_path.c, oracle/cpu_backend.py), the baseline
+bench.py times next to the GPU path.  The reference's CPU path cannot be built here, so these are known-answer checks of
+the restated mathematics: the sparse matrix rows are normalised, a unit volume simulates to 1, and the whole loop
+recovers the phantom about as well as the GPU algorithm's oracle does."""
+import numpy as np
+
+from fetalreconstruction_b200.phantom import make_dataset, small_config
+from fetalreconstruction_b200.pipeline import SVRPipeline, SVRParams, upload_dataset
+from oracle.cpu_backend import CpuPathReconstruction
+from oracle.oracle_backend import OracleReconstruction
+
+
+def test_coefficients_and_unit_volume():
+    ds = make_dataset(small_config(seed=5, vol=36, n_stacks=2, slices=6, size=30, inplane=1.1, spacing=2.2))
+    b = CpuPathReconstruction()
+    upload_dataset(b, ds)
+    b.UpdateScaleVector(np.ones(ds.S, np.float32), np.ones(ds.S, np.float32))
+    inside = b.coeff_init()
+    assert inside.any() and b.nnz > 20 * (ds.slices != -1).sum()
+    b.recon = np.ones(b.V, np.float32)
+    b.simslices = np.zeros(b.NP, np.float32); b.simweights = np.zeros(b.NP, np.float32); b.siminside = np.zeros(b.NP, np.int8)
+    b.SimulateSlices()
+    valid = (ds.slices.ravel() != -1) & (b.simweights > 0)
+    assert valid.sum() > 0.9 * (ds.slices != -1).sum()
+    # rows are normalised: PSF /= sum and trilinear weights / their in-volume sum (irtkReconstructionGPU.cc:2420, 2520-2560);
+    # pixels whose PSF leaves the mask-touching neighbourhood lose a little mass
+    assert np.median(b.simweights[valid]) > 0.999 and b.simweights[valid].max() <= 1.0 + 1e-5
+    assert np.allclose(b.simslices[valid], 1.0, atol=1e-5)
+    # adjointness of simulate (A) and the super-resolution scatter (A^T): <A x, y> == <x, A^T y>
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0.5, 1.5, b.V).astype(np.float32)
+    b.recon = x
+    b.SimulateSlices()
+    Ax_unnorm = (b.simslices * b.simweights)[valid].astype(np.float64)
+    y = rng.uniform(0.5, 1.5, b.NP).astype(np.float32)
+    b.weights = y.copy(); b.slices = np.where(ds.slices.ravel() != -1, 1.0, -1.0).astype(np.float32)
+    b.simslices = np.zeros(b.NP, np.float32)                     # residual = slice*scale - 0 -> "ss > 0" false -> 0: use cmap = A^T y
+    b.superresolution_local(np.ones(ds.S, np.float32))
+    cmap = b.acc.reshape(-1, 2)[:, 1].astype(np.float64)
+    lhs = float((Ax_unnorm * y[valid]).sum())
+    rhs = float((x.astype(np.float64) * cmap).sum())
+    yv = y.copy(); yv[~(ds.slices.ravel() != -1)] = 0
+    assert abs(lhs - rhs) / abs(rhs) < 1e-4 or abs(float((Ax_unnorm * yv[valid]).sum()) - rhs) / abs(rhs) < 1e-4
+
+
+def test_cpu_path_reconstructs_the_phantom():
+    cfg = small_config()
+    ds = make_dataset(cfg)
+    out = {}
+    for name, b in (("cpu_path", CpuPathReconstruction()), ("gpu_algorithm", OracleReconstruction())):
+        upload_dataset(b, ds)
+        p = SVRPipeline(b, ds.S, 0, ds.S, params=SVRParams(iterations=1, rec_iterations_last=4))
+        p.InitializeEMGPU(ds.slices)
+        out[name] = p.run()
+    m = ds.mask.ravel() != 0
+    truth = ds.truth.ravel()[m].astype(np.float64)
+    err = {k: np.sqrt(np.mean((v[m] - truth) ** 2)) / np.sqrt(np.mean(truth ** 2)) for k, v in out.items()}
+    assert np.isfinite(out["cpu_path"]).all()
+    assert err["cpu_path"] < 0.25 and err["cpu_path"] < 2.5 * err["gpu_algorithm"], err
