@@ -1,0 +1,120 @@
+"""PVRreconstructionGPU (host/pvr_main.cc) as far as it runs without a GPU: option parsing and error behaviour, and the
+set-up pipeline of irtkPatchBasedReconstruction<T>::run() (irtkPatchBasedReconstruction.cpp:194-399: crop to the mask, mask
+resampled to the isotropic grid, intensity matching, template, patch enumeration with the 1/3-coverage rule) checked through
+`--dump_patches` against the Python restatement of PatchBasedVolume::generate2DPatches
+(fetalreconstruction_b200.pvr.generate_2d_patches, which the oracle-pinned PVR tests use).  The device part of the CLI is
+exercised on the GPU box (tests/test_gpu_cli.py)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_host_cli import HOST, run, write_nifti
+
+CLI = os.path.join(HOST, "PVRreconstructionGPU")
+
+
+@pytest.fixture(scope="module")
+def cli(built_lib):
+    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
+    r = subprocess.run(["make", "-C", HOST, "CXX=/usr/bin/g++"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return CLI
+
+
+def make_acquisition(d, seed=5, vol=48, n_stacks=3, slices=14, size=44):
+    from fetalreconstruction_b200.phantom import make_dataset, small_config
+    cfg = small_config(seed=seed, vol=vol, n_stacks=n_stacks, slices=slices, size=size, inplane=1.1, spacing=2.5)
+    cfg.motion_mm = cfg.motion_deg = 0.0
+    cfg.noise = 0.0
+    cfg.corrupt_fraction = 0.0
+    cfg.mask_semi_axis = 0.36
+    ds = make_dataset(cfg)
+    names = []
+    for s, attr in enumerate(ds.stack_attrs):
+        sl = ds.slices[s * slices:(s + 1) * slices]
+        vol_s = np.where(sl == -1, 0.0, sl).astype(np.float32)              # PVR stacks carry 0 background
+        p = os.path.join(d, f"stack_{s}.nii")
+        write_nifti(p, vol_s, attr.image_to_world(), (attr.dx, attr.dy, attr.dz))
+        names.append(p)
+    mp = os.path.join(d, "mask.nii")
+    write_nifti(mp, ds.mask.astype(np.float32), ds.vol_attr.image_to_world(), (cfg.vol_voxel,) * 3)
+    return dict(names=names, mask_path=mp, ds=ds, cfg=cfg)
+
+
+@pytest.fixture(scope="module")
+def acquisition(tmp_path_factory):
+    return make_acquisition(str(tmp_path_factory.mktemp("pvr_acq")))
+
+
+def test_pvr_cli_option_errors(cli, acquisition, tmp_path):
+    a = acquisition
+    assert run(cli, ["--help"], tmp_path).returncode == 0
+    r = run(cli, ["-i", "a.nii"], tmp_path)
+    assert r.returncode != 0 and "--output" in r.stderr
+    r = run(cli, ["-o", "o.nii", "-i", "a.nii", "--bogus"], tmp_path)
+    assert r.returncode != 0 and "unrecognised option" in r.stderr
+    r = run(cli, ["-o", "o.nii", "-i", "a.nii", "--superpixel"], tmp_path)
+    assert r.returncode != 0 and "not supported" in r.stderr
+    r = run(cli, ["-o", "o.nii", "-i", "missing.nii", "-m", a["mask_path"]], tmp_path)
+    assert r.returncode != 0 and "cannot read" in r.stderr
+    r = run(cli, ["-o", "o.nii", "-i"] + a["names"], tmp_path)                # no mask
+    assert r.returncode != 0 and "mask" in r.stderr
+    r = run(cli, ["-o", "o.nii", "-i"] + a["names"] + ["-m", a["mask_path"], "--patchSize", "128", "128"], tmp_path)
+    assert r.returncode != 0 and "64" in r.stderr
+
+
+def _attr(v):
+    from fetalreconstruction_b200.geometry import ImageAttributes
+    return ImageAttributes(int(v[0]), int(v[1]), int(v[2]), v[3], v[4], v[5], v[6:9].copy(), v[9:12].copy(), v[12:15].copy(), v[15:18].copy())
+
+
+def test_patch_enumeration_matches_python_restatement(cli, acquisition, tmp_path):
+    from fetalreconstruction_b200.pvr import generate_2d_patches
+    a = acquisition
+    out = tmp_path / "dump"
+    out.mkdir()
+    r = run(cli, ["-o", "recon.nii.gz", "-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--patchSize", "16", "16",
+                  "--patchStride", "8", "8", "--dump_patches", str(out)], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    idx = dict(line.split() for line in open(out / "index.txt"))
+    n_stacks, n = int(idx["stacks"]), int(idx["patches"])
+    per_stack = np.fromfile(out / "per_stack.i32", np.int32)
+    i2w = np.fromfile(out / "i2w.f32", np.float32).reshape(n, 4, 4)
+    w2i = np.fromfile(out / "w2i.f32", np.float32).reshape(n, 4, 4)
+    T = np.fromfile(out / "T.f32", np.float32).reshape(n, 4, 4)
+    assert n_stacks == 3 and per_stack.sum() == n and np.all(per_stack > 0)
+    assert np.allclose(T, np.eye(4)[None])
+    assert np.allclose(np.einsum("nij,njk->nik", i2w.astype(np.float64), w2i.astype(np.float64)), np.eye(4)[None], atol=1e-3)
+
+    mv = np.fromfile(out / "mask_attr.f64", np.float64)
+    mattr = _attr(mv)
+    mask = np.fromfile(out / "mask.f64", np.float64).reshape(mattr.z, mattr.y, mattr.x)
+    assert set(np.unique(mask)) <= {0.0, 1.0} and mask.sum() > 0
+    assert abs(mattr.dx - 1.0) < 1e-12                                           # resampled to --resolution
+    start = 0
+    averages = []
+    for s in range(n_stacks):
+        sv = np.fromfile(out / f"stack{s}_attr.f64", np.float64)
+        sattr, thickness = _attr(sv), sv[18]
+        assert thickness == pytest.approx(sattr.dz)                              # default: dz, slices get 2 * dz (patchBasedReconMain.cpp:212-215)
+        stack = np.fromfile(out / f"stack{s}.f64", np.float64).reshape(sattr.z, sattr.y, sattr.x)
+        assert sattr.z <= a["cfg"].slices_per_stack and sattr.x <= 44              # cropped to the mask
+        attrs, cube = generate_2d_patches(stack.astype(np.float32), sattr, (mask > 0).astype(np.int8), mattr, (16, 16), (8, 8), thickness=thickness)
+        # pixel coordinates that land exactly on a voxel boundary truncate either way (the two hosts compose the same
+        # matrices in a different order), which can move a patch across the 1/3 threshold: allow 2 % of the patches to differ
+        want = np.stack([p.image_to_world() for p in attrs])
+        got = i2w[start:start + per_stack[s]].astype(np.float64)
+        assert abs(len(attrs) - per_stack[s]) <= max(1, 0.02 * len(attrs)), (s, len(attrs), per_stack[s])
+        d = np.abs(got[:, None, :, 3] - want[None, :, :, 3]).max(-1)             # match patches by their origin column
+        matched = (d.min(1) < 1e-3).sum()
+        assert matched >= 0.98 * max(len(attrs), per_stack[s]), (s, matched, len(attrs), per_stack[s])
+        j = d.argmin(1)
+        ok = d.min(1) < 1e-3
+        assert np.abs(got[ok] - want[j[ok]]).max() < 1e-3
+        start += per_stack[s]
+        averages.append(stack[stack > 0].mean())
+    # intensity matching pulls the in-mask averages of the stacks together (irtkPatchBasedReconstruction.cpp:656-789)
+    assert max(averages) / min(averages) < 1.1
+    assert float(idx["max"]) > float(idx["min"]) > 0
