@@ -131,7 +131,7 @@ def recorded_traffic():
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_sample_dataset(cfg, per_stack=8):
+def cpu_sample_dataset(cfg, per_stack=32):
     """A bounded sample of the same workload for the CPU arm: `per_stack` mid-stack slices of one axis-aligned and one
     oblique stack against the full-size volume and mask."""
     from fetalreconstruction_b200.phantom import make_dataset
@@ -196,7 +196,7 @@ def run_cpu_baseline(cfg, steps=1, warmup=0):
     S_full = cfg.n_stacks * cfg.slices_per_stack
     t_full = tv + (t - tv) * S_full / ds.S               # volume-side work (regulariser, masking) does not grow with the slices
     return {"value": ds.S * PROJ_PER_SLICE_STEP / t, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-            "sample": f"{ds.S} mid-stack slices (8 of an axis-aligned + 8 of an oblique stack) of the {cfg.name} workload, full "
+            "sample": f"{ds.S} mid-stack slices ({ds.S // 2} of an axis-aligned + {ds.S // 2} of an oblique stack) of the {cfg.name} workload, full "
                       f"{cfg.vol_size[0]}^3 volume, one outer iteration (10 slice-projections per slice), {t:.1f} s per step, of which "
                       f"{tv:.1f} s volume-side (regulariser) that does not grow with the number of slices.  The port is the reference's "
                       "CPU (--useCPU) formulation -- sparse slice-to-volume matrix of CoeffInit (Gaussian PSF, trilinear splat, "
