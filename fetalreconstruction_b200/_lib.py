@@ -68,6 +68,7 @@ _SIGNATURES = {
     "svr_profile_reset": (ip, [vp]),
     "svr_reg_init_storage": (ip, [vp, ip, ip, ip, fp, fp, fp]),
     "svr_reg_fill_slices": (ip, [vp, vp, vp]),
+    "svr_reg_resample_slices": (ip, [vp, vp, vp, vp, vp]),
     "svr_reg_update_slices_i2w": (ip, [vp, vp]),
     "svr_reg_prepare": (ip, [vp]),
     "svr_reg_set_schedule": (ip, [vp, ip, ip, ip]),

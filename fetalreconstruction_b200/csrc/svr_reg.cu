@@ -550,6 +550,90 @@ int svr_reg_fill_slices(svr_context* c, const float* cube, const float* slices_r
     return 0;
 }
 
+// irtkResamplingWithPadding::Run for single-plane slices (irtkResamplingWithPadding.cc:36-183), one thread per output
+// pixel, double precision, no FMA contraction and the host's operation order (bit-identical to the host front-end):
+// neighbours equal to the padding value are dropped and the remaining weights renormalised; out-of-bounds neighbours
+// count as not padded but add nothing; the result is padding when >= 4 of the 8 neighbours are padding or the weight
+// sum is 0.
+__global__ void __launch_bounds__(256)
+reg_resample_kernel(int S, int W, int H, int Nx, int Ny, const float* __restrict__ slices, const double* __restrict__ m,
+                    const int* __restrict__ in_sizes, const int* __restrict__ out_sizes, float* __restrict__ out)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t P = (size_t)W * H;
+    if (idx >= P * S) return;
+    const int s = (int)(idx / P), pix = (int)(idx - (size_t)s * P);
+    const int j = pix / W, i = pix - j * W;
+    if (i >= out_sizes[2 * s] || j >= out_sizes[2 * s + 1]) { out[idx] = -1.0f; return; }
+    const int ax = in_sizes[2 * s], ay = in_sizes[2 * s + 1];
+    const double* q = m + 12 * (size_t)s;
+    const double di = (double)i, dj = (double)j;
+    const double x = __dadd_rn(__dadd_rn(__dmul_rn(q[0], di), __dmul_rn(q[1], dj)), q[3]);
+    const double y = __dadd_rn(__dadd_rn(__dmul_rn(q[4], di), __dmul_rn(q[5], dj)), q[7]);
+    const double z = __dadd_rn(__dadd_rn(__dmul_rn(q[8], di), __dmul_rn(q[9], dj)), q[11]);
+    const double fu = floor(x), fv = floor(y), fw = floor(z);
+    const int u = (int)fu, v = (int)fv, w = (int)fw;
+    const double dx = __dadd_rn(x, -fu), dy = __dadd_rn(y, -fv), dz = __dadd_rn(z, -fw);
+    const float* img = slices + (size_t)s * Nx * Ny;
+    double val = 0.0, wsum = 0.0;
+    int pad = 8;
+#pragma unroll
+    for (int du = 0; du < 2; ++du)
+#pragma unroll
+        for (int dv = 0; dv < 2; ++dv)
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw) {
+                const int uu = u + du, vv = v + dv, ww = w + dw;
+                const bool inb = uu >= 0 && uu < ax && vv >= 0 && vv < ay && ww >= 0 && ww < 1;
+                const double g = inb ? (double)img[(size_t)vv * Nx + uu] : -1.0;
+                const bool good = inb && g != -1.0;
+                const double wx = du ? dx : __dadd_rn(1.0, -dx), wy = dv ? dy : __dadd_rn(1.0, -dy), wz = dw ? dz : __dadd_rn(1.0, -dz);
+                const double wt = __dmul_rn(__dmul_rn(wx, wy), wz);
+                if (good) { val = __dadd_rn(val, __dmul_rn(g, wt)); wsum = __dadd_rn(wsum, wt); }
+                if (!inb || good) --pad;
+            }
+    out[idx] = (pad < 4 && wsum > 0.0) ? (float)__ddiv_rn(val, wsum) : -1.0f;
+}
+
+int svr_reg_resample_slices(svr_context* c, const double* src_from_out, const int* in_sizes, const int* out_sizes,
+                            const float* slices_resampled_i2w)
+{
+    if (!c) return 2;
+    RegState* r = (RegState*)c->reg;
+    REG_REQUIRE(c, r, "svr_reg_resample_slices: call svr_reg_init_storage first");
+    REG_REQUIRE(c, r->S == c->S, "svr_reg_resample_slices: the registration cube and the slice cube hold different numbers of slices");
+    const int S = r->S;
+    if (S == 0 || (size_t)r->W * r->H == 0) { r->have_slices = true; return 0; }
+    REG_REQUIRE(c, c->slices, "svr_reg_resample_slices: call svr_init_storage_volumes / svr_fill_slices first");
+    REG_REQUIRE(c, src_from_out && in_sizes && out_sizes, "svr_reg_resample_slices: NULL argument");
+    for (int s = 0; s < S; ++s) {
+        REG_REQUIRE(c, in_sizes[2 * s] >= 0 && in_sizes[2 * s] <= c->Nx && in_sizes[2 * s + 1] >= 0 && in_sizes[2 * s + 1] <= c->Ny,
+                    "svr_reg_resample_slices: slice extent outside the slice cube");
+        REG_REQUIRE(c, out_sizes[2 * s] >= 0 && out_sizes[2 * s] <= r->W && out_sizes[2 * s + 1] >= 0 && out_sizes[2 * s + 1] <= r->H,
+                    "svr_reg_resample_slices: resampled extent outside the registration cube");
+    }
+    SVR_CUDA(c, cudaSetDevice(c->device));
+    double* d_m = nullptr;
+    int* d_sz = nullptr;
+    SVR_CUDA(c, cudaMalloc(&d_m, sizeof(double) * 12 * S));
+    if (cudaMalloc(&d_sz, sizeof(int) * 4 * S) != cudaSuccess) { cudaFree(d_m); c->err = "svr_reg_resample_slices: out of device memory"; return 1; }
+    cudaMemcpyAsync(d_m, src_from_out, sizeof(double) * 12 * S, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_sz, in_sizes, sizeof(int) * 2 * S, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_sz + 2 * S, out_sizes, sizeof(int) * 2 * S, cudaMemcpyHostToDevice, c->stream);
+    if (slices_resampled_i2w)
+        cudaMemcpyAsync(r->res_i2w, slices_resampled_i2w, sizeof(float) * 16 * S, cudaMemcpyHostToDevice, c->stream);
+    const size_t n = (size_t)r->W * r->H * S;
+    reg_resample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(S, r->W, r->H, c->Nx, c->Ny, c->slices, d_m, d_sz, d_sz + 2 * S,
+                                                                           r->resampled);
+    c->launches++;
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_m);
+    cudaFree(d_sz);
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { c->err = "svr_reg_resample_slices: kernel failed"; return 1; }
+    r->have_slices = true;
+    return 0;
+}
+
 int svr_reg_update_slices_i2w(svr_context* c, const float* ofs)
 {
     if (!c) return 2;

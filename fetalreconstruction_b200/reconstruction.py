@@ -227,6 +227,15 @@ class Reconstruction:
         m = None if slices_resampledI2W is None else _f32(slices_resampledI2W, (self.regS, 16))
         self._ck(self._lib.svr_reg_fill_slices(self._h, _p(cube), _p(m)))
 
+    def resampleRegSlices(self, src_from_out, in_sizes, out_sizes, slices_resampledI2W=None):
+        """Device form of PrepareRegistrationSlices' resampling (svr_reg_resample_slices): the slices uploaded by
+        FillSlices are resampled on the device into the registration cube.  src_from_out [S,4,4] float64."""
+        m = np.ascontiguousarray(np.asarray(src_from_out, np.float64).reshape(self.regS, 4, 4)[:, :3, :].reshape(self.regS, 12))
+        a = np.ascontiguousarray(in_sizes, np.int32).reshape(self.regS, 2)
+        o = np.ascontiguousarray(out_sizes, np.int32).reshape(self.regS, 2)
+        i2w = None if slices_resampledI2W is None else _f32(slices_resampledI2W, (self.regS, 16))
+        self._ck(self._lib.svr_reg_resample_slices(self._h, _p(m), _p(a), _p(o), _p(i2w)))
+
     def updateResampledSlicesI2W(self, ofsSlice):
         m = _f32(ofsSlice, (self.regS, 16))
         self._ck(self._lib.svr_reg_update_slices_i2w(self._h, _p(m)))

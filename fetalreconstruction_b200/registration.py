@@ -63,21 +63,30 @@ def resample_plane0_with_padding(img: np.ndarray, attr: ImageAttributes, out_att
 class RegistrationFrontEnd:
     """PrepareRegistrationSlices + SliceToVolumeRegistrationGPU for the slices of one rank."""
 
-    def __init__(self, backend, slices: np.ndarray, slice_attrs: list[ImageAttributes], recon_voxel: float):
+    def __init__(self, backend, slices: np.ndarray, slice_attrs: list[ImageAttributes], recon_voxel: float,
+                 slices_resident: bool = False):
+        """`slices_resident`: the CUDA backend already holds exactly these slices (FillSlices); otherwise they are
+        uploaded first (the reference resamples its host copies of the slices it uploaded, irtkReconstructionGPU.cc:1992-2059)."""
         self.b = backend
         self.d = float(recon_voxel)
         self.res_attrs = [resampled_attributes(a, self.d) for a in slice_attrs]
         S = len(slice_attrs)
         W = max([a.x for a in self.res_attrs], default=1)
         H = max([a.y for a in self.res_attrs], default=1)
-        cube = np.full((S, H, W), -1.0, np.float32)
-        for k, (a, ra) in enumerate(zip(slice_attrs, self.res_attrs)):
-            cube[k, :ra.y, :ra.x] = resample_plane0_with_padding(slices[k, :a.y, :a.x], a, ra)
-        self.cube = cube
         i2w = np.stack([ra.image_to_world().astype(np.float32).ravel() for ra in self.res_attrs]) if S else np.zeros((0, 16), np.float32)
         d0 = (self.d, self.d, self.d)
         backend.initRegStorageVolumes((W, H, S), d0)
-        backend.FillRegSlices(cube.ravel(), i2w)
+        self._cube = None
+        if hasattr(backend, "resampleRegSlices"):
+            # the CUDA backend resamples the slices it already holds (FillSlices) on the device
+            if not slices_resident and S:
+                backend.FillSlices(np.asarray(slices).ravel())
+            m = np.stack([a.world_to_image() @ ra.image_to_world() for a, ra in zip(slice_attrs, self.res_attrs)]) if S else np.zeros((0, 4, 4))
+            backend.resampleRegSlices(m, [(a.x, a.y) for a in slice_attrs], [(ra.x, ra.y) for ra in self.res_attrs], i2w)
+        else:
+            # the CPU twins (oracle, reference adapter: test infrastructure) take the host-resampled cube
+            self._cube = self.resample_on_host(slices, slice_attrs)
+            backend.FillRegSlices(self._cube.ravel(), i2w)
         # origin reset (irtkReconstructionGPU.cc:2226-2250)
         self.mo = []
         ofs = np.zeros((S, 16), np.float32)
@@ -88,6 +97,22 @@ class RegistrationFrontEnd:
             z = ImageAttributes(ra.x, ra.y, ra.z, ra.dx, ra.dy, ra.dz, np.zeros(3), ra.xaxis, ra.yaxis, ra.zaxis)
             ofs[k] = z.image_to_world().astype(np.float32).ravel()
         self.ofs = ofs
+
+    def resample_on_host(self, slices, slice_attrs) -> np.ndarray:
+        S = len(slice_attrs)
+        W = max([a.x for a in self.res_attrs], default=1)
+        H = max([a.y for a in self.res_attrs], default=1)
+        cube = np.full((S, H, W), -1.0, np.float32)
+        for k, (a, ra) in enumerate(zip(slice_attrs, self.res_attrs)):
+            cube[k, :ra.y, :ra.x] = resample_plane0_with_padding(slices[k, :a.y, :a.x], a, ra)
+        return cube
+
+    @property
+    def cube(self) -> np.ndarray:
+        """The resampled slices [S][H][W] (read back from the device when they were resampled there)."""
+        if self._cube is None:
+            self._cube = self.b.debugRegSlices(blurred=False).copy()
+        return self._cube
 
     def pack_transforms(self, transformations: np.ndarray) -> np.ndarray:
         """_transf[i] = toMatrix4(T_i * mo_i)"""

@@ -457,31 +457,51 @@ static Image resample_slice_with_padding(const Image& in, double d, double paddi
 }
 
 // ---- PrepareRegistrationSlices, irtkReconstructionGPU.cc:2105-2179 --------------------------------------------------
+// The reference resamples its host copies of the slices and uploads them (FillRegSlices); the slices are already on the
+// device here (SyncGPU), so the resampling runs there (svr_reg_resample_slices: same rules, double precision, on the
+// float32 slices the device holds: within one float ulp of resampling the host's double copies).  With --debug the host
+// form above is evaluated as well and the largest difference is printed.
 void Reconstruction::PrepareRegistrationSlices()
 {
     const int S = (int)slices_.size();
     const double d = reconstructed_.a.dx;
-    std::vector<Image> res;
-    res.reserve(S);
     res_attrs_.clear();
     regW_ = regH_ = 0;
     int minx = INT_MAX, miny = INT_MAX;
     for (const Image& s : slices_) {
-        res.push_back(resample_slice_with_padding(s, d, -1));
-        res_attrs_.push_back(res.back().a);
-        regW_ = std::max(regW_, res.back().a.x); regH_ = std::max(regH_, res.back().a.y);
-        minx = std::min(minx, res.back().a.x); miny = std::min(miny, res.back().a.y);
+        res_attrs_.push_back(resampled_attr(s.a, d, d, d));
+        const ImageAttr& ra = res_attrs_.back();
+        regW_ = std::max(regW_, ra.x); regH_ = std::max(regH_, ra.y);
+        minx = std::min(minx, ra.x); miny = std::min(miny, ra.y);
     }
     const double waste = ((double)(regW_ - minx) * (regH_ - miny) * S) * sizeof(double) * 5.0 / 1024.0;
     std::printf("GPU memory waste approx RegSlices: %f KB with %d %d %d %d\n", waste, regW_, regH_, minx, miny);
     ck(svr_reg_init_storage(c_, regW_, regH_, S, (float)d, (float)d, (float)d), "initRegStorageVolumes");
-    std::vector<float> cube((size_t)regW_ * regH_ * S, -1.0f), i2w(16 * (size_t)S);
+    std::vector<double> m(12 * (size_t)S);
+    std::vector<int> in_sizes(2 * (size_t)S), out_sizes(2 * (size_t)S);
+    std::vector<float> i2w(16 * (size_t)S);
     for (int n = 0; n < S; ++n) {
-        const Image& s = res[n];
-        for (int y = 0; y < s.a.y; ++y) for (int x = 0; x < s.a.x; ++x) cube[((size_t)n * regH_ + y) * regW_ + x] = (float)s.at(x, y, 0);
-        s.a.image_to_world().to_float16(&i2w[16 * n]);
+        const Mat4 mm = slices_[n].a.world_to_image() * res_attrs_[n].image_to_world();
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 4; ++q) m[12 * (size_t)n + 4 * r + q] = mm.m[r][q];
+        in_sizes[2 * n] = slices_[n].a.x; in_sizes[2 * n + 1] = slices_[n].a.y;
+        out_sizes[2 * n] = res_attrs_[n].x; out_sizes[2 * n + 1] = res_attrs_[n].y;
+        res_attrs_[n].image_to_world().to_float16(&i2w[16 * n]);
     }
-    ck(svr_reg_fill_slices(c_, cube.data(), i2w.data()), "FillRegSlices");
+    ck(svr_reg_resample_slices(c_, m.data(), in_sizes.data(), out_sizes.data(), i2w.data()), "resampleRegSlices");
+    if (debug && S > 0) {
+        std::vector<float> cube((size_t)regW_ * regH_ * S);
+        ck(svr_reg_debug_get(c_, 0, cube.data()), "debugRegSlices");
+        // the device resamples the float32 slices it was given, the host form its double copies: up to one float ulp apart
+        double worst = 0;
+        for (int n = 0; n < S; n += std::max(1, S / 8)) {          // a sample of the slices
+            const Image h = resample_slice_with_padding(slices_[n], d, -1);
+            for (int y = 0; y < h.a.y; ++y) for (int x = 0; x < h.a.x; ++x) {
+                const double a = (double)(float)h.at(x, y, 0), b = (double)cube[((size_t)n * regH_ + y) * regW_ + x];
+                worst = std::max(worst, std::fabs(a - b) / std::max(1.0, std::fabs(a)));
+            }
+        }
+        std::cout << "registration slices: device vs host resampling, max relative difference " << worst << std::endl;
+    }
     reg_prepared_ = true;
 }
 

@@ -122,6 +122,17 @@ int svr_reg_init_storage(svr_context *ctx, int W, int H, int S, float dx, float 
 /* ref: FillRegSlices(float* sdata, vector<Matrix4> slices_resampledI2W) .cuh:328, cuda2.cu:5023-5088.
  * cube = float[S][H][W], -1 = padding.  The matrices are stored but, as in the reference, not used. */
 int svr_reg_fill_slices(svr_context *ctx, const float *cube, const float *slices_resampled_i2w /* [S][16] or NULL */);
+/* Device form of the resampling that feeds FillRegSlices: irtkReconstruction::PrepareRegistrationSlices
+ * (irtkReconstructionGPU.cc:1992-2059) resamples every slice to the reconstruction's voxel size with
+ * irtkResamplingWithPadding (IRTKSimple2/image++/src/irtkResamplingWithPadding.cc:36-183, padding -1) on the host and
+ * uploads the result.  Here the slices uploaded by svr_fill_slices are resampled in place on the device, in double
+ * precision and in the reference's order of operations, into the registration cube of svr_reg_init_storage:
+ *   src_from_out [S][12]  rows 0..2 of (slice world-to-image) x (resampled slice image-to-world), double
+ *   in_sizes     [S][2]   valid extent (x, y) of slice s inside the packed slice cube
+ *   out_sizes    [S][2]   extent (x, y) of the resampled slice; the rest of its [H][W] plane is padding
+ * Equivalent to svr_reg_fill_slices with the host-resampled cube. */
+int svr_reg_resample_slices(svr_context *ctx, const double *src_from_out, const int *in_sizes, const int *out_sizes,
+                            const float *slices_resampled_i2w /* [S][16] or NULL */);
 /* ref: updateResampledSlicesI2W(vector<Matrix4> ofsSlice) .cuh:330, cuda2.cu:4707-4757: image-to-world of
  * the resampled slices with their origin reset to 0 (irtkReconstructionGPU.cc:2226-2250). */
 int svr_reg_update_slices_i2w(svr_context *ctx, const float *ofs_slice /* [S][16] */);

@@ -112,3 +112,16 @@ def test_pvr_cli_end_to_end_matches_python_host(built_lib, tmp_path):
     for got in (vol, vol0):                      # no registration between the passes: every pass reconstructs the same volume
         d = np.abs(got - want) / scale
         assert np.sqrt(np.mean(d ** 2)) <= 1e-4 and d.max() <= 1e-2, (np.sqrt(np.mean(d ** 2)), d.max())
+
+
+def test_cli_registration_pass_uses_device_resampling(cli, acquisition, tmp_path):
+    """Two outer iterations: the second starts with SliceToVolumeRegistrationGPU, whose input slices are resampled on the
+    device (svr_reg_resample_slices); --debug makes the host evaluate the same rules and print the largest difference."""
+    a = acquisition
+    r = run(cli, ["-o", "recon.nii.gz", "-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0",
+                  "--iterations", "2", "--rec_iterations_first", "2", "--rec_iterations_last", "2", "--debug", "1", "--no_log", "1"], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if "device vs host resampling" in l]
+    assert lines, r.stdout[-2000:]
+    assert float(lines[0].rsplit(" ", 1)[1]) <= 2e-7, lines[0]      # one float ulp: the device holds the slices as float32
+    assert (tmp_path / "image1_GPU.nii.gz").exists() and (tmp_path / "recon.nii.gz").exists()

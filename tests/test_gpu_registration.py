@@ -110,3 +110,44 @@ def test_registration_empty_and_errors():
     g.updateResampledSlicesI2W(np.zeros((0, 16), np.float32))
     g.prepareSliceToVolumeReg()
     assert g.registerSlicesToVolume(np.zeros((0, 16), np.float32)).shape == (0, 16)
+
+
+def test_device_resampling_matches_host_rules_on_ragged_padded_slices():
+    """svr_reg_resample_slices against the host restatement of irtkResamplingWithPadding (registration.py) on slices of
+    different sizes with padding islands and a padded border, bit for bit; and its argument checks."""
+    from fetalreconstruction_b200.geometry import ImageAttributes
+    from fetalreconstruction_b200.reconstruction import Reconstruction, SVRError
+    from fetalreconstruction_b200.registration import resample_plane0_with_padding, resampled_attributes
+    rng = np.random.default_rng(11)
+    Nx, Ny, S, d = 37, 29, 5, 0.8
+    sizes = [(37, 29), (30, 29), (37, 20), (11, 7), (1, 1)]
+    attrs, cube = [], np.full((S, Ny, Nx), -1.0, np.float32)
+    for k, (sx, sy) in enumerate(sizes):
+        attrs.append(ImageAttributes(sx, sy, 1, 1.0 + 0.13 * k, 0.9 + 0.07 * k, 2.5, rng.normal(0, 5, 3)))
+        img = rng.uniform(1, 100, (sy, sx)).astype(np.float32)
+        img[rng.uniform(size=img.shape) < 0.15] = -1.0                         # padding islands
+        img[:, : sx // 6] = -1.0                                               # padded border
+        cube[k, :sy, :sx] = img
+    res = [resampled_attributes(a, d) for a in attrs]
+    W, H = max(r.x for r in res), max(r.y for r in res)
+    want = np.full((S, H, W), -1.0, np.float32)
+    for k, (a, r) in enumerate(zip(attrs, res)):
+        want[k, :r.y, :r.x] = resample_plane0_with_padding(cube[k, :a.y, :a.x], a, r)
+    g = Reconstruction(0)
+    g.InitReconstructionVolume((8, 8, 8), (d, d, d), None)
+    g.initStorageVolumes((Nx, Ny, S))
+    g.FillSlices(cube.ravel())
+    g.initRegStorageVolumes((W, H, S), (d, d, d))
+    m = np.stack([a.world_to_image() @ r.image_to_world() for a, r in zip(attrs, res)])
+    g.resampleRegSlices(m, [(a.x, a.y) for a in attrs], [(r.x, r.y) for r in res])
+    got = g.debugRegSlices()
+    assert (want != -1).sum() > 500 and ((want == -1) & (np.arange(W)[None, None, :] < np.array([r.x for r in res])[:, None, None])).sum() > 50
+    assert np.array_equal(got, want)
+    with pytest.raises(SVRError):                                              # extent outside the slice cube
+        g.resampleRegSlices(m, [(Nx + 1, Ny)] * S, [(r.x, r.y) for r in res])
+    with pytest.raises(SVRError):                                              # extent outside the registration cube
+        g.resampleRegSlices(m, [(a.x, a.y) for a in attrs], [(W + 1, H)] * S)
+    g2 = Reconstruction(0)
+    g2.regS, g2.regW, g2.regH = S, W, H
+    with pytest.raises(SVRError):                                              # no registration storage yet
+        g2.resampleRegSlices(m, [(a.x, a.y) for a in attrs], [(r.x, r.y) for r in res])
