@@ -9,13 +9,16 @@
 //   * the patch-to-volume registration between iterations (patchBased2D3DRegistration::runHybrid, IRTK on the CPU) and
 //     the 3D stack-to-stack registration are not restated: patches keep the -t transformation of
 //     their stack, so every pass of the iteration loop reconstructs from the same geometry;
-//   * --superpixel (SLICO superpixels, runStackSLIC.cpp), --hierarchical, --resample (B-spline), --packages,
-//     --useFullSlices and the evaluation options are refused; a mask (-m) is required.
+//   * --hierarchical, --resample (B-spline), --packages, --useFullSlices and the evaluation options are refused; a mask
+//     (-m) is required.
+// --superpixel runs SLICO per slice on the host (pvr_slic.cc) and cuts one 64 x 64 patch per superpixel with its
+// char[64*64] mask (PatchBasedVolume::generate2DSuperpixelPatches, include/patchBasedObject.cuh:433-797).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -26,6 +29,7 @@
 #include <vector>
 
 #include "../include/pvr_abi.h"
+#include "pvr_slic.h"
 #include "svr_image.h"
 #include "svr_reconstruction.h"
 
@@ -44,7 +48,8 @@ struct Options {
     std::vector<int> devices;
     double resolution = 0.75;
     int iterations = 7, sr_iterations = 7, dilateMask = 0;
-    bool noMatchIntensities = false, debug = false;
+    bool noMatchIntensities = false, debug = false, superpixel = false;
+    unsigned spxSize = 16, spxExtend = 50;                                     // patchBasedReconMain.cpp:105-106
 };
 
 void usage()
@@ -66,8 +71,10 @@ void usage()
         "  -d [ --devices ] arg             GPU to use (one device per process)\n"
         "  --thickness arg                  [th_1] .. [th_N] patch thickness. [Default: twice voxel size in z direction]\n"
         "  --debug                          Write debug images.\n"
-        "  -s [ --superpixel ] / --spxSize / --spxExtend / --hierarchical / --resample / --useFullSlices / -p [ --packages ]\n"
-        "                                   (not supported by this build)\n"
+        "  -s [ --superpixel ]              Turn on superpixel-based reconstruction. [Default: false]\n"
+        "  --spxSize arg                    initial size (<=64) of the 2D superpixels [Default: 16]\n"
+        "  --spxExtend arg                  ratio [0-100]% of a superpixel's size for dilation / overlap [Default: 50%]\n"
+        "  --hierarchical / --resample / --useFullSlices / -p [ --packages ]   (not supported by this build)\n"
         "  --dump_patches arg               (this build only) write the enumerated patches (matrices, counts, cropped stacks,\n"
         "                                   resampled mask) into directory arg and exit; needs no GPU.\n";
 }
@@ -115,7 +122,10 @@ bool parse(int argc, char** argv, Options& o, bool& help)
         else if (a == "--devices") { values(vs); for (auto& s : vs) o.devices.push_back(atoi(s.c_str())); }
         else if (a == "--thickness") { values(vs); for (auto& s : vs) o.thickness.push_back(atof(s.c_str())); }
         else if (a == "--dump_patches") { if (!one(a, o.dump_patches)) return false; }
-        else if (a == "--superpixel" || a == "--spxSize" || a == "--spxExtend" || a == "--hierarchical" || a == "--resample" ||
+        else if (a == "--superpixel") o.superpixel = true;
+        else if (a == "--spxSize") { if (!one(a, v)) return false; o.spxSize = (unsigned)atoi(v.c_str()); }
+        else if (a == "--spxExtend") { if (!one(a, v)) return false; o.spxExtend = (unsigned)atoi(v.c_str()); }
+        else if (a == "--hierarchical" || a == "--resample" ||
                  a == "--useFullSlices" || a == "--packages" || a == "--evaluateGt" || a == "--evaluation" || a == "--evaluateBaseline" ||
                  a == "--patchExtraction")
             return unsupported(a);
@@ -126,6 +136,11 @@ bool parse(int argc, char** argv, Options& o, bool& help)
         o.patchStride[1] == 0) {
         std::cerr << "ERROR: --patchSize and --patchStride take two positive values" << std::endl;
         return false;
+    }
+    if (o.superpixel) {                                  // patchBasedReconMain.cpp:289-296
+        if (o.spxSize == 0 || o.spxSize > 64 || o.spxExtend > 100) { std::cerr << "ERROR: --spxSize is 1..64 and --spxExtend 0..100" << std::endl; return false; }
+        o.patchSize = { o.spxSize, o.spxSize };
+        o.patchStride = { o.spxExtend, o.spxExtend };
     }
     if (o.patchSize[0] > 64 || o.patchSize[1] > 64) {      // the device patch cube and the 64x64 superpixel mask layout (reconConfig.cuh)
         std::cerr << "ERROR: patches are at most 64 x 64" << std::endl;
@@ -211,6 +226,10 @@ Image resample_nn(const Image& src, double d)
 
 struct Patches {                      // one stack
     std::vector<float> i2w, w2i;      // 16 floats per patch
+    std::vector<char> spx;            // superpixel mode: char[64*64] per patch, '1' = pixel belongs to the patch
+    int pbx = 0, pby = 0;             // superpixel mode: the patch size used (64 x 64 clamped to the stack)
+    std::vector<int> labels;          // superpixel mode: SLICO labels [z][y][x] (for --dump_patches)
+    std::vector<int> label_of_patch;  // superpixel mode: (slice, label) per patch
     int count = 0;
     long long total_pixels = 0;
 };
@@ -262,6 +281,113 @@ Patches generate_2d_patches(const Image& stack, const Image& mask, int pbx, int 
                     out.total_pixels += set_count;
                 }
             }
+        }
+    }
+    return out;
+}
+
+// PatchBasedVolume::generate2DSuperpixelPatches, include/patchBasedObject.cuh:433-797: SLICO labels per slice, then one
+// patch per label: the label's bounding box grown to the (fixed 64 x 64, clamped to the stack) patch window, the label's
+// pixels inside the mask dilated by spxExtend % of the larger box side (4-neighbourhood), and the result stored as the
+// patch's char[64*64] mask.  Quirks kept: the largest label of a slice is never visited (`idxLbl < int(maxLbl)`, :510),
+// labels with fewer than max(2, spx area / 4) masked pixels are dropped (:668-669), dilated pixels whose centre falls
+// outside the slice or the mask grid stay in the mask (:708-721).
+Patches generate_superpixel_patches(const Image& stack, const Image& mask, unsigned spx_x, unsigned spx_y, unsigned extend_pct, double thickness)
+{
+    Patches out;
+    const ImageAttr& attr = stack.a;
+    if ((int)spx_x > attr.x) { std::printf("WARNING: spxSize.x is bigger than imageSize.x - force spxSize.x = 0.5 * imageSize.x \n"); spx_x = attr.x / 2; }
+    if ((int)spx_y > attr.y) { std::printf("WARNING: spxSize.y is bigger than imageSize.y - force spxSize.y = 0.5 * imageSize.y \n"); spx_y = attr.y / 2; }
+    float vmin = std::numeric_limits<float>::max(), vmax = -std::numeric_limits<float>::max();
+    for (double v : stack.v) { vmin = std::min(vmin, (float)v); vmax = std::max(vmax, (float)v); }
+    std::printf("min: %f \nmax: %f \n", vmin, vmax);
+    const float dilate_ratio = (float)extend_pct / 100.f;
+    const int pbx = std::min(64, attr.x), pby = std::min(64, attr.y);
+    out.pbx = pbx; out.pby = pby;
+    std::printf("Dilation ratio: %d %% \nMax patch size - after dilation - %d x %d \n", extend_pct, pbx, pby);
+    const Mat4 stack_i2w = attr.image_to_world();
+    const Mat4 mask_w2i = mask.a.world_to_image();
+    std::vector<float> slice((size_t)attr.x * attr.y);
+    std::vector<int> cell((size_t)pbx * pby), grown;
+    for (int z = 0; z < attr.z; ++z) {
+        for (int y = 0; y < attr.y; ++y) for (int x = 0; x < attr.x; ++x) slice[(size_t)y * attr.x + x] = (float)stack.at(x, y, z);
+        int n_labels = 0;
+        const std::vector<int> labels = svr::slico_labels(slice.data(), attr.x, attr.y, vmin, vmax, spx_x, spx_y, &n_labels);
+        out.labels.insert(out.labels.end(), labels.begin(), labels.end());
+        int min_lbl = INT_MAX, max_lbl = INT_MIN;
+        for (int l : labels) { min_lbl = std::min(min_lbl, l); max_lbl = std::max(max_lbl, l); }
+        for (int lbl = min_lbl; lbl < max_lbl; ++lbl) {
+            int x_min = INT_MAX, y_min = INT_MAX, x_max = INT_MIN, y_max = INT_MIN;
+            for (int y = 0; y < attr.y; ++y) for (int x = 0; x < attr.x; ++x)
+                if (labels[(size_t)y * attr.x + x] == lbl) { x_min = std::min(x_min, x); x_max = std::max(x_max, x); y_min = std::min(y_min, y); y_max = std::max(y_max, y); }
+            if (x_min == INT_MAX) continue;
+            const int box_x = x_max - x_min, box_y = y_max - y_min;
+            const int diter = (int)(dilate_ratio * (float)std::max(box_x, box_y));
+            const int ext_x = (int)std::round(((float)pbx - (float)box_x) / 2.f), ext_y = (int)std::round(((float)pby - (float)box_y) / 2.f);
+            if (x_min - ext_x < 0) { x_max = pbx; x_min = 0; }
+            else if (x_max + ext_x > attr.x) { x_max = attr.x; x_min = x_max - pbx; }
+            else { x_min -= ext_x; x_max = x_min + pbx; }
+            if (y_min - ext_y < 0) { y_max = pby; y_min = 0; }
+            else if (y_max + ext_y > attr.y) { y_max = attr.y; y_min = y_max - pby; }
+            else { y_min -= ext_y; y_max = y_min + pby; }
+
+            // the patch image: GetRegion(x_min, y_min, z, x_max, y_max, z + 1) with dz = 2 * thickness (:590-591)
+            ImageAttr pa = attr;
+            pa.x = x_max - x_min; pa.y = y_max - y_min; pa.z = 1;
+            pa.dz = thickness * 2;
+            double cx = (x_min + x_max - 1) / 2.0, cy = (y_min + y_max - 1) / 2.0, cz = z;
+            stack_i2w.apply(cx, cy, cz);
+            pa.origin[0] = cx; pa.origin[1] = cy; pa.origin[2] = cz;
+            const Mat4 p_i2w = pa.image_to_world();
+            const Mat4 m_m = mask_w2i * p_i2w;
+            // per patch pixel: 0 = outside the slice / the mask grid (stays what dilation makes of it), 1 = usable
+            auto in_grids = [&](int i, int j, bool& masked) {
+                const int xx = x_min + i, yy = y_min + j;           // the patch is an axis-aligned window of its slice
+                double xm = i, ym = j, zm = 0;
+                m_m.apply(xm, ym, zm);
+                xm = std::round(xm); ym = std::round(ym); zm = std::round(zm);
+                masked = false;
+                if (!(xx >= 0 && yy >= 0 && xx < attr.x && yy < attr.y)) return false;
+                if (!(xm >= 0 && ym >= 0 && zm >= 0 && xm < mask.a.x && ym < mask.a.y && zm < mask.a.z)) return false;
+                masked = mask.at((int)xm, (int)ym, (int)zm) > 0;
+                return true;
+            };
+            int set_count = 0;
+            for (int j = 0; j < pby; ++j) for (int i = 0; i < pbx; ++i) {
+                bool masked;
+                int v = 0;
+                if (i < pa.x && j < pa.y && in_grids(i, j, masked) && masked) v = labels[(size_t)(y_min + j) * attr.x + (x_min + i)] == lbl ? 1 : 0;
+                cell[(size_t)j * pbx + i] = v;
+                set_count += v;
+            }
+            if (set_count < 2) continue;
+            if (set_count < 1.0f / 4.0f * spx_y * spx_x) continue;
+            for (int it = 0; it < diter; ++it) {                      // dilatePatch (:347-368): 4-neighbourhood
+                grown = cell;
+                for (int j = 0; j < pby; ++j) for (int i = 0; i < pbx; ++i) {
+                    if (cell[(size_t)j * pbx + i] != 1) continue;
+                    if (i > 0) grown[(size_t)j * pbx + i - 1] = 1;
+                    if (j > 0) grown[(size_t)(j - 1) * pbx + i] = 1;
+                    if (i + 1 < pbx) grown[(size_t)j * pbx + i + 1] = 1;
+                    if (j + 1 < pby) grown[(size_t)(j + 1) * pbx + i] = 1;
+                }
+                cell.swap(grown);
+            }
+            std::vector<char> spx(4096, '0');
+            for (int j = 0; j < pby; ++j) for (int i = 0; i < pbx; ++i) {
+                if (cell[(size_t)j * pbx + i] == 0) continue;
+                bool masked;
+                const bool inside = i < pa.x && j < pa.y && in_grids(i, j, masked);
+                if (inside && !masked) continue;                       // inside the grids but outside the mask: -1
+                spx[i + 64 * j] = '1';
+                out.total_pixels++;
+            }
+            float m[16];
+            p_i2w.to_float16(m); out.i2w.insert(out.i2w.end(), m, m + 16);
+            pa.world_to_image().to_float16(m); out.w2i.insert(out.w2i.end(), m, m + 16);
+            out.spx.insert(out.spx.end(), spx.begin(), spx.end());
+            out.label_of_patch.push_back(z); out.label_of_patch.push_back(lbl);
+            out.count++;
         }
     }
     return out;
@@ -328,7 +454,7 @@ int main(int argc, char** argv)
             }
         }
         if (template_num < 0) throw std::runtime_error("at least one stack needs the 'id' transformation (the template)");
-        std::cout << "patch-based ON" << std::endl << "cuda_dev = " << device << std::endl;
+        std::cout << (o.superpixel ? "superpixel-based ON" : "patch-based ON") << std::endl << "cuda_dev = " << device << std::endl;
 
         // ---- run(): mask, crop, resample (irtkPatchBasedReconstruction.cpp:197-266) ----------------------------------------
         Image mask;
@@ -374,14 +500,22 @@ int main(int argc, char** argv)
         helper.TransformMask(recon, reconmask, transformations[template_num]);
 
         // ---- patches (:391-399, patchBasedObject.cuh:176-342) ---------------------------------------------------------------
-        const int pbx = (int)o.patchSize[0], pby = (int)o.patchSize[1];
+        int pbx = (int)o.patchSize[0], pby = (int)o.patchSize[1];
+        std::vector<char> spx_masks;
         std::vector<Patches> patches(stacks.size());
         std::vector<int> pps(stacks.size());
         std::vector<float> stack_dims(3 * stacks.size()), i2w, w2i, T, Ti;
         for (size_t i = 0; i < stacks.size(); ++i) {
             std::cout << "stack [" << i << "] -------------------------- " << std::endl;
             std::printf("Thickness %f \n", thickness[i]);
-            patches[i] = generate_2d_patches(stacks[i], mask, pbx, pby, (int)o.patchStride[0], (int)o.patchStride[1], thickness[i]);
+            if (o.superpixel) {
+                patches[i] = generate_superpixel_patches(stacks[i], mask, o.patchSize[0], o.patchSize[1], o.patchStride[0], thickness[i]);
+                if (i > 0 && (patches[i].pbx != pbx || patches[i].pby != pby))
+                    throw std::runtime_error("superpixel mode: the stacks clamp the 64 x 64 patch window differently (a stack is smaller than 64 pixels)");
+                pbx = patches[i].pbx; pby = patches[i].pby;
+                spx_masks.insert(spx_masks.end(), patches[i].spx.begin(), patches[i].spx.end());
+            } else
+                patches[i] = generate_2d_patches(stacks[i], mask, pbx, pby, (int)o.patchStride[0], (int)o.patchStride[1], thickness[i]);
             std::printf("m_patches GPU size: %d ... \n", patches[i].count);
             pps[i] = patches[i].count;
             stack_dims[3 * i] = (float)stacks[i].a.dx; stack_dims[3 * i + 1] = (float)stacks[i].a.dy; stack_dims[3 * i + 2] = (float)stacks[i].a.dz;
@@ -393,7 +527,7 @@ int main(int argc, char** argv)
             for (int p = 0; p < patches[i].count; ++p) { T.insert(T.end(), m, m + 16); Ti.insert(Ti.end(), mi, mi + 16); }
         }
         const size_t n_patches = i2w.size() / 16;
-        if (n_patches == 0) throw std::runtime_error("no patch passed the 1/3-coverage rule: check the mask and the transformations");
+        if (n_patches == 0) throw std::runtime_error("no patch passed the coverage rule: check the mask and the transformations");
 
         float rw2i[16], ri2w[16];
         recon.a.world_to_image().to_float16(rw2i);
@@ -412,6 +546,7 @@ int main(int argc, char** argv)
             write_raw(d + "/i2w.f32", i2w.data(), i2w.size() * 4);
             write_raw(d + "/w2i.f32", w2i.data(), w2i.size() * 4);
             write_raw(d + "/T.f32", T.data(), T.size() * 4);
+            if (o.superpixel) write_raw(d + "/spx.i8", spx_masks.data(), spx_masks.size());
             write_raw(d + "/recon_w2i.f32", rw2i, 64);
             write_raw(d + "/recon_i2w.f32", ri2w, 64);
             write_raw(d + "/recon_mask.i8", mask8.data(), mask8.size());
@@ -432,6 +567,10 @@ int main(int argc, char** argv)
                 sa.push_back(thickness[i]);
                 write_raw(d + "/stack" + std::to_string(i) + "_attr.f64", sa.data(), sa.size() * 8);
                 write_raw(d + "/stack" + std::to_string(i) + ".f64", stacks[i].v.data(), stacks[i].v.size() * 8);
+                if (o.superpixel) {
+                    write_raw(d + "/labels" + std::to_string(i) + ".i32", patches[i].labels.data(), patches[i].labels.size() * 4);
+                    write_raw(d + "/label_of_patch" + std::to_string(i) + ".i32", patches[i].label_of_patch.data(), patches[i].label_of_patch.size() * 4);
+                }
             }
             std::cout << "patches written to " << d << std::endl;
             return EXIT_SUCCESS;
@@ -451,6 +590,7 @@ int main(int argc, char** argv)
         }
         ck(pvr_patches_init(c, pbx, pby, (int)stacks.size(), pps.data(), stack_dims.data()), "PatchBasedVolume::init");
         ck(pvr_patches_set_matrices(c, i2w.data(), w2i.data(), T.data(), Ti.data()), "patch matrices");
+        if (o.superpixel) ck(pvr_patches_set_spx_masks(c, spx_masks.data(), 1), "superpixel masks");
         {
             ImageAttr pa;                                   // PSF image: PSF_SIZE^3 voxels of the reconstruction's size (:404-419)
             pa.x = pa.y = pa.z = 128;
@@ -507,7 +647,7 @@ int main(int argc, char** argv)
             Image reconimage(recon.a);
             for (size_t q = 0; q < out.size(); ++q) reconimage.v[q] = out[q];
             char buffer[256];
-            std::snprintf(buffer, sizeof(buffer), "reconimage%i_%i_%i.nii.gz", iter, pbx, (int)o.patchStride[0]);
+            std::snprintf(buffer, sizeof(buffer), "reconimage%i_%i_%i.nii.gz", iter, (int)o.patchSize[0], (int)o.patchStride[0]);
             write_or_die(buffer, reconimage, true);
             std::cout << "----------------------------------------------------------------------------------------------------------------" << std::endl;
         }

@@ -57,7 +57,8 @@ def test_cli_end_to_end_matches_python_host(cli, acquisition, tmp_path):
     assert np.allclose(np.abs(np.linalg.det(aff[:3, :3])), 1.0, atol=1e-4)
 
 
-def test_pvr_cli_end_to_end_matches_python_host(built_lib, tmp_path):
+@pytest.mark.parametrize("superpixel", [False, True])
+def test_pvr_cli_end_to_end_matches_python_host(built_lib, tmp_path, superpixel):
     """host/PVRreconstructionGPU: NIfTI stacks in, reconimage<iter>_<size>_<stride>.nii.gz + the -o volume out, against the
     Python PVRPipeline (the one pinned to the reference's PVR code in test_ref_golden.py) fed with the patches the CLI itself
     enumerated (`--dump_patches`): both sides then issue the same device calls in the same order."""
@@ -68,25 +69,29 @@ def test_pvr_cli_end_to_end_matches_python_host(built_lib, tmp_path):
     env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
     r = subprocess.run(["make", "-C", os.path.dirname(PVR_CLI), "CXX=/usr/bin/g++"], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
-    a = make_acquisition(str(tmp_path))
-    common = ["-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--patchSize", "16", "16", "--patchStride", "8", "8",
-                                    "--iterations", "1", "--sr_iterations", "2"]
+    if superpixel:           # SLICO superpixels of ~12 x 12 pixels, masks dilated by 25 %, 64 x 64 patch windows
+        a = make_acquisition(str(tmp_path), seed=9, vol=72, n_stacks=2, slices=6, size=76)
+        shape, tag = ["--superpixel", "--spxSize", "12", "--spxExtend", "25"], "12_25"
+    else:
+        a = make_acquisition(str(tmp_path))
+        shape, tag = ["--patchSize", "16", "16", "--patchStride", "8", "8"], "16_8"
+    common = ["-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0"] + shape + ["--iterations", "1", "--sr_iterations", "2"]
     dump = tmp_path / "dump"
     dump.mkdir()
     r = run(PVR_CLI, ["-o", "pvr.nii.gz"] + common + ["--dump_patches", str(dump)], tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     r = run(PVR_CLI, ["-o", "pvr.nii.gz"] + common, tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
-    for name in ("reconimage0_16_8.nii.gz", "reconimage1_16_8.nii.gz", "pvr.nii.gz"):
+    for name in (f"reconimage0_{tag}.nii.gz", f"reconimage1_{tag}.nii.gz", "pvr.nii.gz"):
         assert (tmp_path / name).exists(), name
     (tmp_path / "pvr.nii").write_bytes(gzip.open(tmp_path / "pvr.nii.gz").read())
     vol, aff, meta = read_nifti(tmp_path / "pvr.nii")
     assert meta["datatype"] == 16 and np.isfinite(vol).all() and (vol != 0).any()
-    (tmp_path / "it0.nii").write_bytes(gzip.open(tmp_path / "reconimage0_16_8.nii.gz").read())
+    (tmp_path / "it0.nii").write_bytes(gzip.open(tmp_path / f"reconimage0_{tag}.nii.gz").read())
     vol0 = read_nifti(tmp_path / "it0.nii")[0]
 
     idx = dict(line.split() for line in open(dump / "index.txt"))
-    n, S = int(idx["patches"]), int(idx["stacks"])
+    n, S, pbx, pby = int(idx["patches"]), int(idx["stacks"]), int(idx["pbx"]), int(idx["pby"])
     vx, vy, vz = int(idx["vx"]), int(idx["vy"]), int(idx["vz"])
     assert vol.shape == (vz, vy, vx)
     b = PatchReconstruction(0)
@@ -98,10 +103,12 @@ def test_pvr_cli_end_to_end_matches_python_host(built_lib, tmp_path):
         sv = np.fromfile(dump / f"stack{s}_attr.f64", np.float64)
         sattrs.append(_attr(sv))
         stacks.append(np.fromfile(dump / f"stack{s}.f64", np.float64).reshape(sattrs[-1].z, sattrs[-1].y, sattrs[-1].x).astype(np.float32))
-    b.patches_init(16, 16, np.fromfile(dump / "per_stack.i32", np.int32), [(t.dx, t.dy, t.dz) for t in sattrs])
+    b.patches_init(pbx, pby, np.fromfile(dump / "per_stack.i32", np.int32), [(t.dx, t.dy, t.dz) for t in sattrs])
     T = np.fromfile(dump / "T.f32", np.float32).reshape(n, 16)
     b.patches_set_matrices(np.fromfile(dump / "i2w.f32", np.float32).reshape(n, 16), np.fromfile(dump / "w2i.f32", np.float32).reshape(n, 16),
                            T, np.stack([np.linalg.inv(t.reshape(4, 4).astype(np.float64)).astype(np.float32).ravel() for t in T]))
+    if superpixel:
+        b.patches_set_spx(np.fromfile(dump / "spx.i8", "S1").reshape(n, 4096), True)
     psf = ImageAttributes(128, 128, 128, 1.0, 1.0, 1.0)
     b.set_psf((128, 128, 128), psf.image_to_world().astype(np.float32).ravel(), 1.0)
     for s in range(S):

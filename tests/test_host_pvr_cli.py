@@ -55,7 +55,7 @@ def test_pvr_cli_option_errors(cli, acquisition, tmp_path):
     assert r.returncode != 0 and "--output" in r.stderr
     r = run(cli, ["-o", "o.nii", "-i", "a.nii", "--bogus"], tmp_path)
     assert r.returncode != 0 and "unrecognised option" in r.stderr
-    r = run(cli, ["-o", "o.nii", "-i", "a.nii", "--superpixel"], tmp_path)
+    r = run(cli, ["-o", "o.nii", "-i", "a.nii", "--hierarchical"], tmp_path)
     assert r.returncode != 0 and "not supported" in r.stderr
     r = run(cli, ["-o", "o.nii", "-i", "missing.nii", "-m", a["mask_path"]], tmp_path)
     assert r.returncode != 0 and "cannot read" in r.stderr
@@ -118,3 +118,85 @@ def test_patch_enumeration_matches_python_restatement(cli, acquisition, tmp_path
     # intensity matching pulls the in-mask averages of the stacks together (irtkPatchBasedReconstruction.cpp:656-789)
     assert max(averages) / min(averages) < 1.1
     assert float(idx["max"]) > float(idx["min"]) > 0
+
+
+def _components(lab2d):
+    """Number of 4-connected components per label value."""
+    from scipy import ndimage
+    out = {}
+    for v in np.unique(lab2d):
+        out[int(v)] = ndimage.label(lab2d == v)[1]
+    return out
+
+
+def test_superpixel_mode_labels_and_masks(cli, tmp_path):
+    """--superpixel: SLICO labels per slice (host/pvr_slic.cc, after runStackSLIC.cpp) and one masked 64 x 64 patch per
+    superpixel (generate2DSuperpixelPatches, patchBasedObject.cuh:433-797), checked through `--dump_patches`: every label is
+    one 4-connected region of about the requested size, labels follow a strong intensity edge, each patch window contains
+    its superpixel, the mask holds the superpixel's in-mask pixels plus a dilation margin and nothing else."""
+    a = make_acquisition(str(tmp_path), seed=9, vol=72, n_stacks=2, slices=6, size=76)
+    # a strong vertical edge through stack 0 so that boundary adherence can be seen
+    from test_host_cli import read_nifti
+    data, aff, _ = read_nifti(a["names"][0])
+    data = data.copy()
+    data[:, :, data.shape[2] // 2:] *= 3.0
+    write_nifti(a["names"][0], data, aff, (1.1, 1.1, 2.5))
+    out = tmp_path / "dump"
+    out.mkdir()
+    spx = 12
+    r = run(cli, ["-o", "recon.nii.gz", "-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--superpixel", "--spxSize", str(spx),
+                  "--spxExtend", "25", "--noMatchIntensities", "--dump_patches", str(out)], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "superpixel-based ON" in r.stdout
+    idx = dict(line.split() for line in open(out / "index.txt"))
+    n, pbx, pby = int(idx["patches"]), int(idx["pbx"]), int(idx["pby"])
+    assert (pbx, pby) == (64, 64) or (pbx <= 64 and pby <= 64)
+    per_stack = np.fromfile(out / "per_stack.i32", np.int32)
+    masks = np.fromfile(out / "spx.i8", "S1").reshape(n, 64, 64)                 # [patch][j][i], index i + 64 * j
+    assert set(np.unique(masks)) <= {b"0", b"1"}
+    i2w = np.fromfile(out / "i2w.f32", np.float32).reshape(n, 4, 4).astype(np.float64)
+    mattr = _attr(np.fromfile(out / "mask_attr.f64", np.float64))
+    mask = np.fromfile(out / "mask.f64", np.float64).reshape(mattr.z, mattr.y, mattr.x)
+    m_w2i = mattr.world_to_image()
+    start = 0
+    for s in range(2):
+        sv = np.fromfile(out / f"stack{s}_attr.f64", np.float64)
+        sattr = _attr(sv)
+        stack = np.fromfile(out / f"stack{s}.f64", np.float64).reshape(sattr.z, sattr.y, sattr.x)
+        labels = np.fromfile(out / f"labels{s}.i32", np.int32).reshape(sattr.z, sattr.y, sattr.x)
+        lop = np.fromfile(out / f"label_of_patch{s}.i32", np.int32).reshape(-1, 2)
+        assert len(lop) == per_stack[s] and per_stack[s] > 0
+        s_w2i = sattr.world_to_image()
+        for z in range(sattr.z):
+            lab = labels[z]
+            comps = _components(lab)
+            assert all(c == 1 for c in comps.values()), (s, z, comps)            # connectivity enforced
+            sizes = np.bincount(lab.ravel())
+            expected = sattr.x * sattr.y / (spx * spx)
+            assert 0.4 * expected <= len(sizes) <= 2.5 * expected, (len(sizes), expected)
+            assert sizes.min() > (spx * spx) // 4 // 2                               # small segments were merged away
+            if s == 0:
+                # boundary adherence: few superpixels straddle the 3x intensity edge
+                hi = stack[z] > 2.0 * np.median(stack[z][stack[z] > 0]) if (stack[z] > 0).any() else np.zeros_like(lab, bool)
+                both = sum(1 for v in range(len(sizes)) if 0.1 < hi[lab == v].mean() < 0.9)
+                assert both <= 0.15 * len(sizes), (both, len(sizes))
+        # patches of this stack
+        for q in range(per_stack[s]):
+            z, lbl = lop[q]
+            msk = masks[start + q] == b"1"
+            jj, ii = np.nonzero(msk)
+            assert len(ii) >= 2 and ii.max() < pbx and jj.max() < pby
+            # patch pixel -> stack pixel through the matrices the device receives
+            pts = np.stack([ii, jj, np.zeros_like(ii), np.ones_like(ii)], 1).astype(np.float64)
+            world = pts @ i2w[start + q].T
+            sp = np.rint(world @ s_w2i.T).astype(int)
+            assert np.all(sp[:, 2] == z)
+            inside = (sp[:, 0] >= 0) & (sp[:, 0] < sattr.x) & (sp[:, 1] >= 0) & (sp[:, 1] < sattr.y)
+            assert inside.mean() > 0.99
+            own = labels[z][sp[inside, 1], sp[inside, 0]] == lbl
+            assert own.sum() >= (spx * spx) / 4 - 1                                  # the superpixel itself (>= 1/4 of the requested area)
+            assert own.mean() > 0.25                                                  # plus a dilation margin, not the whole window
+            mv = np.floor(world @ m_w2i.T + 0.5).astype(int)
+            okm = (mv[:, 0] >= 0) & (mv[:, 0] < mattr.x) & (mv[:, 1] >= 0) & (mv[:, 1] < mattr.y) & (mv[:, 2] >= 0) & (mv[:, 2] < mattr.z)
+            assert np.all(mask[mv[okm, 2], mv[okm, 1], mv[okm, 0]] > 0)                # nothing outside the reconstruction mask
+        start += per_stack[s]
