@@ -366,14 +366,16 @@ def main():
                                                   if k in alg_bytes and v[0] > 0 else None}
                                 for k, v in prof.items()}}
         # what does bound these kernels: the warp schedulers' issue slots.  Tap count of one K2 launch (pixels that carry a
-        # PSF sum x 16^3 taps) x the SASS instructions per tap of the shipped loop (349 per 16-tap row)
-        # against 4 issue slots per SM per clock; ncu reports the same ~87 % as smsp__issue_active (profiles/).
-        if dom == "simulate" and dom_ms > 0:
+        # PSF sum x 16^3 taps) x the SASS instructions per tap of the per-pixel loop (349 per 16-tap row)
+        # against 4 issue slots per SM per clock.  ncu's smsp__issue_active is ~87 % on stacks whose pixel rows run along
+        # the volume's x; stacks in other orientations pay extra (L1 wavefronts; staged rows), which this figure shows.
+        k2_ms = prof["simulate"][0] / max(prof["simulate"][1], 1)
+        if k2_ms > 0:
             n_px = int(np.count_nonzero(backend.debugv_PSF_sums()))
             sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
-            warp_instr_per_s = n_px * 4096.0 * (349.0 / 16.0) / 32.0 / (dom_ms * 1e-3)
+            warp_instr_per_s = n_px * 4096.0 * (349.0 / 16.0) / 32.0 / (k2_ms * 1e-3)
             issue_peak = 148 * 4 * sm_mhz * 1e6
-            roofline["issue_slots"] = {"pixels_per_launch": n_px, "taps_per_s": n_px * 4096.0 / (dom_ms * 1e-3),
+            roofline["issue_slots"] = {"kernel": "simulate_kernel (K2)", "pixels_per_launch": n_px, "taps_per_s": n_px * 4096.0 / (k2_ms * 1e-3),
                                        "sass_instr_per_tap": 349.0 / 16.0, "warp_instr_per_s": warp_instr_per_s,
                                        "peak_warp_instr_per_s": issue_peak, "frac": warp_instr_per_s / issue_peak,
                                        "sm_mhz": sm_mhz}

@@ -45,6 +45,8 @@ struct __align__(16) SliceGeom {
     // rho_{i+1} = rho_i * kappa with rho_i = 2^-(2 dz_i bz0 + bz0^2), kappa = 2^-(2 bz0^2).
     float two_b, bb, kappa;
     int recur;                   // 1 when the recurrence cannot overflow (|bz0| <= 1, |bz0|+|bz1|+|bz2| <= 4)
+    int through_plane_rows;      // 1 when a step along the slice's x moves less than half a voxel along the volume's x:
+                                 // the tap rows (runs along volume x) of a warp's pixels then share no cache lines
 };
 
 struct VolGeom {

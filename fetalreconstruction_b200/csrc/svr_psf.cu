@@ -74,6 +74,11 @@ __global__ void build_geom_kernel(int S, const float* __restrict__ T, const floa
     g.bb = g.bz[0] * g.bz[0];
     g.kappa = exp2f(-2.0f * g.bb);
     g.recur = (fabsf(g.bz[0]) <= 1.0f && fabsf(g.bz[0]) + fabsf(g.bz[1]) + fabsf(g.bz[2]) <= 4.0f) ? 1 : 0;
+    {   // row 0 of comb = d(slice x)/d(voxel): for a rigid map into an isotropic volume it is also, up to scale, the
+        // direction of a slice-x step in voxel space
+        const float nx = sqrtf(comb[0] * comb[0] + comb[1] * comb[1] + comb[2] * comb[2]);
+        g.through_plane_rows = (nx > 0.f && fabsf(comb[0]) < 0.5f * nx) ? 1 : 0;
+    }
     out[k] = g;
 }
 
@@ -375,6 +380,56 @@ int svr_launch_gaussian_scatter(svr_context* c)
 // ---------------------------------------------------------------------------------------------
 // K2: simulateSlicesKernel3D_tex (reconstruction_cuda2.cu:298-404).
 // pack2[v] = {recon[v]*m, m} with m = (mask != 0), so a tap is one predicated 64-bit load + 2 FFMA.
+// Cooperative row staging for K2.  When a slice's pixel rows do not run along the volume's x (sagittal / coronal stacks
+// against an axial template), the 32 pixels of a warp sit on 32 different volume rows: every per-tap load touches 32
+// cache lines and the kernel becomes bound by L1 wavefronts (measured 4.3x the time of an aligned stack).  Here the warp
+// fetches the 32 tap rows of one (oy, oz) step together -- 16 lanes read one pixel's 128-byte row, two rows per load
+// instruction, fully coalesced -- parks them in shared memory (row stride 34 floats: the 64-bit reads of a half-warp
+// hit 16 distinct bank pairs) and every lane then reads its own row from there.  Same taps, same epsilon-skip chain,
+// same order of the per-pixel sums; rejected taps contribute psf = 0 instead of being skipped.
+#ifndef SVR_COOP
+#define SVR_COOP 1
+#endif
+constexpr int COOP_STRIDE = 34;
+
+template <class TR, bool RECUR>
+__device__ __forceinline__ void simulate_rows_coop(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps,
+                                                   const float2* __restrict__ pack2, float* __restrict__ stage, float& sim, float& wsum)
+{
+    static_assert(TR::SUP == 16, "two 16-tap rows per warp-wide load");
+    const int vx = vg.vx, vy = vg.vy;
+    const float bx1 = g.bx[1], by1 = g.by[1], bz1 = g.bz[1];
+    const float bx2 = g.bx[2], by2 = g.by[2], bz2 = g.bz[2];
+    const int lane = threadIdx.x & 31, half = lane >> 4, el = lane & 15;
+    float2* mine = reinterpret_cast<float2*>(stage + lane * COOP_STRIDE);
+#pragma unroll 1
+    for (int oz = -TR::CEN; oz <= TR::SUP - 1 - TR::CEN; ++oz) {
+        const float foz = (float)oz;
+        const float zx = fmaf(foz, bx2, ps.ex), zy = fmaf(foz, by2, ps.ey), zz = fmaf(foz, bz2, ps.ez);
+#pragma unroll 1
+        for (int oy = -TR::CEN; oy <= TR::SUP - 1 - TR::CEN; ++oy) {
+            const float foy = (float)oy;
+            const int v0 = ((ps.cz + oz) * vy + (ps.cy + oy)) * vx + ps.cx - TR::CEN;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int src = 2 * j + half;
+                const int v0s = __shfl_sync(0xffffffffu, v0, src);
+                *reinterpret_cast<float2*>(stage + src * COOP_STRIDE + 2 * el) = __ldg(&pack2[v0s + el]);
+            }
+            __syncwarp();
+            float p[TR::SUP];
+            psf_row_values<TR, RECUR>(g, fmaf(foy, bx1, zx), fmaf(foy, by1, zy), fmaf(foy, bz1, zz), p);
+#pragma unroll
+            for (int i = 0; i < TR::SUP; ++i) {
+                const float2 pm = mine[i];
+                sim = fmaf(p[i], pm.x, sim);
+                wsum = fmaf(p[i], pm.y, wsum);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <class TR>
 __global__ void __launch_bounds__(128, SVR_MINB)
 simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
@@ -383,24 +438,43 @@ simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx
                 unsigned char* __restrict__ siminside, int* __restrict__ slice_inside)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_valid) return;
-    const uint32_t idx = valid_idx[t];
-    const float sume = psf_sums[idx];
-    if (sume == 0.0f) return;
+    uint32_t idx = 0;
+    float sume = 0.0f;
+    if (t < n_valid) { idx = valid_idx[t]; sume = psf_sums[idx]; }
+    const bool alive = sume != 0.0f;
+#if SVR_COOP
+    if (TR::SUP != 16 && !alive) return;           // the cooperative path (SVR only) needs whole warps
+#else
+    if (!alive) return;
+#endif
     const int k = idx / P, pix = idx - k * P;
     const int y = pix / Nx, x = pix - y * Nx;
     const SliceGeom& g = geom[k];
     const PixelSetup ps = pixel_setup<TR>(g, vg, x, y);
 
     float sim = 0.f, wsum = 0.f;
-    auto tap = [&](int, float psf, bool ok, int v) {
-        if (ok) {
-            const float2 pm = __ldg(&pack2[v]);
-            sim = fmaf(psf, pm.x, sim);
-            wsum = fmaf(psf, pm.y, wsum);
+    bool done = false;
+#if SVR_COOP
+    if constexpr (TR::SUP == 16) {
+        __shared__ __align__(16) float stage_all[4][32 * COOP_STRIDE];
+        const bool ok = alive && ps.interior && g.through_plane_rows && g.recur;
+        if (__all_sync(0xffffffffu, ok)) {
+            simulate_rows_coop<TR, true>(g, vg, ps, pack2, stage_all[threadIdx.x >> 5], sim, wsum);
+            done = true;
         }
-    };
-    psf_rows_dispatch<TR>(g, vg, ps, tap, [](int) {});
+        if (!alive) return;
+    }
+#endif
+    if (!done) {
+        auto tap = [&](int, float psf, bool ok, int v) {
+            if (ok) {
+                const float2 pm = __ldg(&pack2[v]);
+                sim = fmaf(psf, pm.x, sim);
+                wsum = fmaf(psf, pm.y, wsum);
+            }
+        };
+        psf_rows_dispatch<TR>(g, vg, ps, tap, [](int) {});
+    }
     const float weight = wsum / sume;
     if (weight > 0.f) {
         simslices[idx] = sim / wsum;              // (sum psf/sume * x) / (sum psf/sume)
