@@ -9,8 +9,7 @@
 //   * the patch-to-volume registration between iterations (patchBased2D3DRegistration::runHybrid, IRTK on the CPU) and
 //     the 3D stack-to-stack registration are not restated: patches keep the -t transformation of
 //     their stack, so every pass of the iteration loop reconstructs from the same geometry;
-//   * --hierarchical, --resample (B-spline), --packages, --useFullSlices and the evaluation options are refused; a mask
-//     (-m) is required.
+//   * --hierarchical, --resample (B-spline), --packages, --useFullSlices and the evaluation options are refused.
 // --superpixel runs SLICO per slice on the host (pvr_slic.cc) and cuts one 64 x 64 patch per superpixel with its
 // char[64*64] mask (PatchBasedVolume::generate2DSuperpixelPatches, include/patchBasedObject.cuh:433-797).
 #include <algorithm>
@@ -57,7 +56,7 @@ void usage()
     std::cout << "Application to perform reconstruction of volumetric MRI from thick patches.\nOptions:\n"
         "  -h [ --help ]                    Print usage messages\n"
         "  -o [ --output ] arg              Name for the reconstructed volume. Nifti format.\n"
-        "  -m [ --mask ] arg                Binary mask to define the region od interest (required by this build).\n"
+        "  -m [ --mask ] arg                Binary mask to define the region od interest. [Default: the overlap of the stacks]\n"
         "  -i [ --input ] arg               [stack_1] .. [stack_N]  The input stacks.\n"
         "  -e [ --existingReconTarget ] arg Set an existing reconstruction as target image.\n"
         "  --patchSize arg                  size of the 2D patches [Default: 32 32]\n"
@@ -421,7 +420,6 @@ int main(int argc, char** argv)
         std::cout << "NOTE: patch-to-volume and stack-to-stack registration are not part of this build; patches keep the -t transformation of their stack"
                   << std::endl;
         if (o.input.empty()) throw std::runtime_error("no input stacks (-i)");
-        if (o.mask.empty()) throw std::runtime_error("a mask (-m) is required: CreateMaskFromOverlap is not part of this build");
         if (!o.transformation.empty() && o.transformation.size() != o.input.size())
             throw std::runtime_error("-t needs one transformation (or 'id') per input stack");
         const bool set_thickness = o.thickness.empty();
@@ -458,7 +456,26 @@ int main(int argc, char** argv)
 
         // ---- run(): mask, crop, resample (irtkPatchBasedReconstruction.cpp:197-266) ----------------------------------------
         Image mask;
-        {
+        if (o.mask.empty()) {
+            // CreateMaskFromOverlap (:968-1004): on the grid of the first stack, 1 where the voxel's world position lies
+            // inside the grid of every stack (the stack transformations are not applied, as in the reference)
+            std::cout << "creating mask from overlap " << std::endl;
+            mask = Image(stacks[0].a, 0.0);
+            const Mat4 i2w = mask.a.image_to_world();
+            std::vector<Mat4> w2i;
+            for (const Image& s : stacks) w2i.push_back(s.a.world_to_image());
+            for (int z = 0; z < mask.a.z; ++z) for (int y = 0; y < mask.a.y; ++y) for (int x = 0; x < mask.a.x; ++x) {
+                double wx = x, wy = y, wz = z;
+                i2w.apply(wx, wy, wz);
+                bool inside = true;
+                for (size_t i = 0; i < stacks.size() && inside; ++i) {
+                    double a = wx, b = wy, c = wz;
+                    w2i[i].apply(a, b, c);
+                    inside = a >= 0 && b >= 0 && c >= 0 && a < stacks[i].a.x && b < stacks[i].a.y && c < stacks[i].a.z;
+                }
+                if (inside) mask.at(x, y, z) = 1;
+            }
+        } else {
             std::string err;
             if (!svr::read_nifti(o.mask, mask, nullptr, &err)) throw std::runtime_error("cannot read " + o.mask + ": " + err);
             for (double& v : mask.v) v = ((unsigned)(signed char)(int)v == 0) ? 0 : 1;      // the mask is read as char (:201-207)

@@ -59,8 +59,15 @@ def test_pvr_cli_option_errors(cli, acquisition, tmp_path):
     assert r.returncode != 0 and "not supported" in r.stderr
     r = run(cli, ["-o", "o.nii", "-i", "missing.nii", "-m", a["mask_path"]], tmp_path)
     assert r.returncode != 0 and "cannot read" in r.stderr
-    r = run(cli, ["-o", "o.nii", "-i"] + a["names"], tmp_path)                # no mask
-    assert r.returncode != 0 and "mask" in r.stderr
+    # no mask: CreateMaskFromOverlap -- the voxels of stack 0 whose centre lies inside every stack's grid
+    out = tmp_path / "nomask"
+    out.mkdir()
+    r = run(cli, ["-o", "o.nii", "-i"] + a["names"] + ["--resolution", "1.0", "--patchSize", "16", "16", "--patchStride", "8", "8",
+                  "--dump_patches", str(out)], tmp_path)
+    assert r.returncode == 0 and "creating mask from overlap" in r.stdout, r.stdout + r.stderr
+    mv = np.fromfile(out / "mask_attr.f64", np.float64)
+    m = np.fromfile(out / "mask.f64", np.float64)
+    assert set(np.unique(m)) == {0.0, 1.0} and 0.02 < m.mean() < 0.9            # three orthogonal stacks: a central box
     r = run(cli, ["-o", "o.nii", "-i"] + a["names"] + ["-m", a["mask_path"], "--patchSize", "128", "128"], tmp_path)
     assert r.returncode != 0 and "64" in r.stderr
 
