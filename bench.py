@@ -222,8 +222,10 @@ def run_reference_cuda(cfg, stacks=1):
     except Exception as e:                                   # the baseline is optional; the bench line is not
         return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
     return {"value": d["S"] * PROJ_PER_SLICE_STEP / d["iteration_s"], "unit": UNIT, "kind": "reference CUDA path on this GPU",
-            "sample": f"{d['S']} slices ({stacks} stack(s) of the C3 workload, full 256^3 volume), one outer iteration after one untimed "
-                      f"warm-up iteration, {d['iteration_s']:.3f} s wall; every call synchronous as in the reference",
+            "sample": f"{d['S']} slices ({stacks} stack(s) of the C3 workload, full 256^3 volume), the fastest of three outer iterations "
+                      f"after one untimed warm-up iteration, {d['iteration_s']:.3f} s wall (all: "
+                      f"{', '.join('%.3f' % v for v in d.get('iterations_s', [d['iteration_s']]))} s; the reference's per-call "
+                      "cudaMalloc/cudaFree make its Superresolution vary); every call synchronous as in the reference",
             "ms_per_call": {k: round(v, 3) for k, v in d["ms_per_call"].items() if v >= 0.05}}
 
 

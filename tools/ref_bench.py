@@ -73,13 +73,21 @@ def run_arm(arm, out, rec_iters, timing_only=False):
     if timing_only:
         # bench.py's reference_cuda leg: one untimed outer iteration (first-call costs of the process: module load, lazy
         # allocations), then the timed one
+        # the reference allocates and frees three volumes in every Superresolution call, whose cost varies wildly from run to
+        # run (30 ms .. 800 ms per call seen on the same box): time three iterations and report the fastest
         p.outer_iteration(0)
-        b.times.clear()
-        t0 = time.perf_counter()
-        p.outer_iteration(0)
-        iter_s = time.perf_counter() - t0
-        print("REFBENCH_JSON " + json.dumps({"arm": arm, "S": int(ds.S), "rec_iters": rec_iters, "iteration_s": iter_s, "setup_s": setup_s,
-                                             "ms_per_call": {k: 1e3 * t / n for k, (t, n) in b.times.items()}}))
+        best = None
+        all_s = []
+        for _ in range(3):
+            b.times.clear()
+            t0 = time.perf_counter()
+            p.outer_iteration(0)
+            iter_s = time.perf_counter() - t0
+            all_s.append(iter_s)
+            if best is None or iter_s < best[0]:
+                best = (iter_s, {k: 1e3 * t / n for k, (t, n) in b.times.items()})
+        print("REFBENCH_JSON " + json.dumps({"arm": arm, "S": int(ds.S), "rec_iters": rec_iters, "iteration_s": best[0], "setup_s": setup_s,
+                                             "iterations_s": all_s, "ms_per_call": best[1]}))
         return
     b.times.clear()
     res = {}
