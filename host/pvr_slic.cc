@@ -127,3 +127,12 @@ std::vector<int> slico_labels(const float* slice, int X, int Y, float vmin, floa
 }
 
 }  // namespace svr
+
+// C entry point for the tests (tests/test_slic_ref.py compares it with the reference's own SLICO code)
+extern "C" int svr_slico_labels(const float* slice, int X, int Y, float vmin, float vmax, unsigned spx0, unsigned spx1, int* labels_out)
+{
+    int n = 0;
+    const std::vector<int> l = svr::slico_labels(slice, X, Y, vmin, vmax, spx0, spx1, &n);
+    for (size_t i = 0; i < l.size(); ++i) labels_out[i] = l[i];
+    return n;
+}
