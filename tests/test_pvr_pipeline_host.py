@@ -12,7 +12,7 @@ from oracle.oracle_backend_pvr import OraclePatchReconstruction
 from pvr_case import make_pvr_case, setup_backend, shard_case
 
 CASE = dict(seed=41, vol=32, n_stacks=2, slices=4, size=32, pbb=(16, 16), stride=(8, 8))
-PARAMS = dict(iterations=1, rec_iterations=2)
+PARAMS = dict(iterations=0, rec_iterations=2)        # one pass: every exchange (P1, P3, EM sums, patch vectors) happens in it
 
 
 def _patch_cube(case):
