@@ -9,7 +9,7 @@
 //   * the patch-to-volume registration between iterations (patchBased2D3DRegistration::runHybrid, IRTK on the CPU) and
 //     the 3D stack-to-stack registration are not restated: patches keep the -t transformation of
 //     their stack, so every pass of the iteration loop reconstructs from the same geometry;
-//   * --hierarchical, --resample (B-spline), --packages, --useFullSlices and the evaluation options are refused.
+//   * --hierarchical, --resample (B-spline), --useFullSlices and the evaluation options are refused.
 // --superpixel runs SLICO per slice on the host (pvr_slic.cc) and cuts one 64 x 64 patch per superpixel with its
 // char[64*64] mask (PatchBasedVolume::generate2DSuperpixelPatches, include/patchBasedObject.cuh:433-797).
 #include <algorithm>
@@ -44,7 +44,7 @@ struct Options {
     std::vector<std::string> input, transformation;
     std::vector<unsigned> patchSize = { 32, 32 }, patchStride = { 16, 16 };   // patchBasedReconMain.cpp:99-102
     std::vector<double> thickness;
-    std::vector<int> devices;
+    std::vector<int> devices, packages;
     double resolution = 0.75;
     int iterations = 7, sr_iterations = 7, dilateMask = 0;
     bool noMatchIntensities = false, debug = false, superpixel = false;
@@ -73,7 +73,9 @@ void usage()
         "  -s [ --superpixel ]              Turn on superpixel-based reconstruction. [Default: false]\n"
         "  --spxSize arg                    initial size (<=64) of the 2D superpixels [Default: 16]\n"
         "  --spxExtend arg                  ratio [0-100]% of a superpixel's size for dilation / overlap [Default: 50%]\n"
-        "  --hierarchical / --resample / --useFullSlices / -p [ --packages ]   (not supported by this build)\n"
+        "  -p [ --packages ] arg            Number of packages used during acquisition for each stack: every stack is split\n"
+        "                                   into that many interleaved sub-stacks, which the reconstruction treats as stacks.\n"
+        "  --hierarchical / --resample / --useFullSlices   (not supported by this build)\n"
         "  --dump_patches arg               (this build only) write the enumerated patches (matrices, counts, cropped stacks,\n"
         "                                   resampled mask) into directory arg and exit; needs no GPU.\n";
 }
@@ -124,8 +126,9 @@ bool parse(int argc, char** argv, Options& o, bool& help)
         else if (a == "--superpixel") o.superpixel = true;
         else if (a == "--spxSize") { if (!one(a, v)) return false; o.spxSize = (unsigned)atoi(v.c_str()); }
         else if (a == "--spxExtend") { if (!one(a, v)) return false; o.spxExtend = (unsigned)atoi(v.c_str()); }
+        else if (a == "--packages") { values(vs); for (auto& q : vs) o.packages.push_back(atoi(q.c_str())); }
         else if (a == "--hierarchical" || a == "--resample" ||
-                 a == "--useFullSlices" || a == "--packages" || a == "--evaluateGt" || a == "--evaluation" || a == "--evaluateBaseline" ||
+                 a == "--useFullSlices" || a == "--evaluateGt" || a == "--evaluation" || a == "--evaluateBaseline" ||
                  a == "--patchExtraction")
             return unsupported(a);
         else { std::cerr << "ERROR: unrecognised option '" << argv[i] << "'" << std::endl; return false; }
@@ -392,6 +395,37 @@ Patches generate_superpixel_patches(const Image& stack, const Image& mask, unsig
     return out;
 }
 
+// patchBasedPackageSplitter<T>::makePackageVolumes (patchBasedPackageSplitter.cpp:78-148): package l of a stack acquired in
+// N interleaved packages holds its slices l, l + N, l + 2N, ... with N times the slice spacing, placed so that its first
+// voxel coincides with voxel (0, 0, l) of the stack; transformation and thickness are inherited.
+void split_into_packages(std::vector<Image>& stacks, std::vector<Rigid>& transformations, std::vector<double>& thickness,
+                         const std::vector<int>& packages)
+{
+    std::vector<Image> out;
+    std::vector<Rigid> out_t;
+    std::vector<double> out_th;
+    for (size_t s = 0; s < stacks.size(); ++s) {
+        const Image& image = stacks[s];
+        const int n = packages[s];
+        const int pkg_z = image.a.z / n;
+        for (int l = 0; l < n; ++l) {
+            ImageAttr attr = image.a;
+            attr.z = (pkg_z * n + l < image.a.z) ? pkg_z + 1 : pkg_z;
+            attr.dz = image.a.dz * n;
+            Image pkg(attr);
+            for (int k = 0; k < attr.z; ++k) for (int j = 0; j < attr.y; ++j) for (int i = 0; i < attr.x; ++i) pkg.at(i, j, k) = image.at(i, j, k * n + l);
+            double x = 0, y = 0, z = l, sx = 0, sy = 0, sz = 0;
+            image.a.image_to_world().apply(x, y, z);
+            pkg.a.image_to_world().apply(sx, sy, sz);
+            pkg.a.origin[0] += x - sx; pkg.a.origin[1] += y - sy; pkg.a.origin[2] += z - sz;
+            out.push_back(std::move(pkg));
+            out_t.push_back(transformations[s]);
+            out_th.push_back(thickness[s]);
+        }
+    }
+    stacks.swap(out); transformations.swap(out_t); thickness.swap(out_th);
+}
+
 void write_raw(const std::string& path, const void* p, size_t bytes)
 {
     FILE* f = std::fopen(path.c_str(), "wb");
@@ -452,6 +486,13 @@ int main(int argc, char** argv)
             }
         }
         if (template_num < 0) throw std::runtime_error("at least one stack needs the 'id' transformation (the template)");
+        if (!o.packages.empty()) {
+            if (o.packages.size() != stacks.size()) throw std::runtime_error("-p needs one package count per input stack");
+            for (int n : o.packages) if (n < 1) throw std::runtime_error("-p: package counts are >= 1");
+            std::printf("splitting volumes into Packages...\n");
+            split_into_packages(stacks, transformations, thickness, o.packages);
+            // as in the reference the template index is the one found before the split (setImageStacks, :97-146)
+        }
         std::cout << (o.superpixel ? "superpixel-based ON" : "patch-based ON") << std::endl << "cuda_dev = " << device << std::endl;
 
         // ---- run(): mask, crop, resample (irtkPatchBasedReconstruction.cpp:197-266) ----------------------------------------

@@ -207,3 +207,38 @@ def test_superpixel_mode_labels_and_masks(cli, tmp_path):
             okm = (mv[:, 0] >= 0) & (mv[:, 0] < mattr.x) & (mv[:, 1] >= 0) & (mv[:, 1] < mattr.y) & (mv[:, 2] >= 0) & (mv[:, 2] < mattr.z)
             assert np.all(mask[mv[okm, 2], mv[okm, 1], mv[okm, 0]] > 0)                # nothing outside the reconstruction mask
         start += per_stack[s]
+
+
+def test_package_splitting(cli, acquisition, tmp_path):
+    """-p: every stack is split into interleaved sub-stacks (patchBasedPackageSplitter.cpp:78-148) -- package l holds slices
+    l, l + N, ... at N times the spacing, placed on the original voxel centres; checked on the cropped stacks of --dump_patches."""
+    from test_host_cli import read_nifti
+    a = acquisition
+    out = tmp_path / "dump"
+    out.mkdir()
+    packages = [2, 3, 1]
+    r = run(cli, ["-o", "o.nii", "-i"] + a["names"] + ["-m", a["mask_path"], "-p"] + [str(p) for p in packages] +
+            ["--resolution", "1.0", "--patchSize", "16", "16", "--patchStride", "8", "8", "--noMatchIntensities", "--dump_patches", str(out)], tmp_path)
+    assert r.returncode == 0 and "splitting volumes into Packages" in r.stdout, r.stdout + r.stderr
+    idx = dict(line.split() for line in open(out / "index.txt"))
+    assert int(idx["stacks"]) == sum(packages)
+    q = 0
+    for s, n in enumerate(packages):
+        data, aff, _ = read_nifti(a["names"][s])
+        inv = np.linalg.inv(aff)
+        seen = set()
+        for l in range(n):
+            sv = np.fromfile(out / f"stack{q}_attr.f64", np.float64)
+            pattr = _attr(sv)
+            pkg = np.fromfile(out / f"stack{q}.f64", np.float64).reshape(pattr.z, pattr.y, pattr.x)
+            assert pattr.dz == pytest.approx(n * 2.5)
+            kk, jj, ii = np.meshgrid(np.arange(pattr.z), np.arange(pattr.y), np.arange(pattr.x), indexing="ij")
+            pts = np.stack([ii.ravel(), jj.ravel(), kk.ravel(), np.ones(ii.size)], 1).astype(np.float64)
+            ijk = pts @ pattr.image_to_world().T @ inv.T
+            r_ijk = np.rint(ijk[:, :3]).astype(int)
+            assert np.abs(ijk[:, :3] - r_ijk).max() < 1e-3                          # on the original voxel centres
+            assert np.all(r_ijk[:, 2] % n == l)                                      # the interleave of package l
+            assert np.array_equal(pkg.ravel(), data[r_ijk[:, 2], r_ijk[:, 1], r_ijk[:, 0]].astype(np.float64))
+            seen |= set(np.unique(r_ijk[:, 2]).tolist())
+            q += 1
+        assert len(seen) > 3                                                         # the packages together cover the cropped slab
