@@ -1,5 +1,6 @@
 """One pass over the hot kernels at the C3 size, for ncu (no timing here; never report numbers taken under a profiler).
-   python tools/profile_c3.py [n_stacks]"""
+   python tools/profile_c3.py [n_stacks]          the first n stacks
+   python tools/profile_c3.py stack=K             stack K alone (e.g. 2 = the through-plane stack of the phantom)"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,9 +9,9 @@ from fetalreconstruction_b200.phantom import make_dataset, c3_config
 from fetalreconstruction_b200.pipeline import SVRPipeline, SVRParams, upload_dataset
 from fetalreconstruction_b200.reconstruction import Reconstruction
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+arg = sys.argv[1] if len(sys.argv) > 1 else "8"
 cfg = c3_config()
-ds = make_dataset(cfg, device="cuda", stacks=range(n))
+ds = make_dataset(cfg, device="cuda", stacks=[int(arg[6:])] if arg.startswith("stack=") else range(int(arg)))
 b = Reconstruction(0)
 upload_dataset(b, ds)
 p = SVRPipeline(b, ds.S, 0, ds.S, params=SVRParams())
