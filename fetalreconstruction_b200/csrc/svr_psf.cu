@@ -392,7 +392,16 @@ int svr_launch_gaussian_scatter(svr_context* c)
 #endif
 constexpr int COOP_STRIDE = 34;
 
-template <class TR, bool RECUR>
+// ZINNER walks oz innermost.  The staged rows of step (oy, oz + 1) are the neighbours' rows of step (oy, oz) when the
+// warp's pixels are neighbours along the volume's z, so with oz innermost they are still in L1 (the ncu capture of the
+// oy-innermost order shows a 3 % L1 hit rate on such a stack: every row comes from L2).  It changes the order of the
+// per-pixel sum, i.e. results agree within tolerance, not bit for bit: compiled only with -DSVR_COOP_ZINNER=1 (an
+// experiment prepared at the end of round 1, not yet measured).
+#ifndef SVR_COOP_ZINNER
+#define SVR_COOP_ZINNER 0
+#endif
+
+template <class TR, bool RECUR, bool ZINNER>
 __device__ __forceinline__ void simulate_rows_coop(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps,
                                                    const float2* __restrict__ pack2, float* __restrict__ stage, float& sim, float& wsum)
 {
@@ -403,12 +412,12 @@ __device__ __forceinline__ void simulate_rows_coop(const SliceGeom& g, const Vol
     const int lane = threadIdx.x & 31, half = lane >> 4, el = lane & 15;
     float2* mine = reinterpret_cast<float2*>(stage + lane * COOP_STRIDE);
 #pragma unroll 1
-    for (int oz = -TR::CEN; oz <= TR::SUP - 1 - TR::CEN; ++oz) {
-        const float foz = (float)oz;
-        const float zx = fmaf(foz, bx2, ps.ex), zy = fmaf(foz, by2, ps.ey), zz = fmaf(foz, bz2, ps.ez);
+    for (int a = -TR::CEN; a <= TR::SUP - 1 - TR::CEN; ++a) {
 #pragma unroll 1
-        for (int oy = -TR::CEN; oy <= TR::SUP - 1 - TR::CEN; ++oy) {
-            const float foy = (float)oy;
+        for (int b = -TR::CEN; b <= TR::SUP - 1 - TR::CEN; ++b) {
+            const int oz = ZINNER ? b : a, oy = ZINNER ? a : b;
+            const float foz = (float)oz, foy = (float)oy;
+            const float zx = fmaf(foz, bx2, ps.ex), zy = fmaf(foz, by2, ps.ey), zz = fmaf(foz, bz2, ps.ez);
             const int v0 = ((ps.cz + oz) * vy + (ps.cy + oy)) * vx + ps.cx - TR::CEN;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -459,7 +468,13 @@ simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx
         __shared__ __align__(16) float stage_all[4][32 * COOP_STRIDE];
         const bool ok = alive && ps.interior && g.through_plane_rows && g.recur;
         if (__all_sync(0xffffffffu, ok)) {
-            simulate_rows_coop<TR, true>(g, vg, ps, pack2, stage_all[threadIdx.x >> 5], sim, wsum);
+#if SVR_COOP_ZINNER
+            // the warp's pixels are neighbours along the slice's x: which volume axis that is decides the loop order
+            if (__all_sync(0xffffffffu, fabsf(g.bx[2]) > fabsf(g.bx[1])))
+                simulate_rows_coop<TR, true, true>(g, vg, ps, pack2, stage_all[threadIdx.x >> 5], sim, wsum);
+            else
+#endif
+            simulate_rows_coop<TR, true, false>(g, vg, ps, pack2, stage_all[threadIdx.x >> 5], sim, wsum);
             done = true;
         }
         if (!alive) return;
