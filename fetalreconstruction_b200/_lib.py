@@ -29,6 +29,7 @@ _SIGNATURES = {
     "svr_set_stream": (ip, [vp, vp]),
     "svr_synchronize": (ip, [vp]),
     "svr_launch_count": (C.c_int64, [vp]),
+    "svr_set_tuning": (ip, [vp, ip, ip]),
     "svr_init_reconstruction_volume": (ip, [vp, ip, ip, ip, fp, fp, fp, vp]),
     "svr_set_mask": (ip, [vp, ip, ip, ip, vp]),
     "svr_init_storage_volumes": (ip, [vp, ip, ip, ip]),

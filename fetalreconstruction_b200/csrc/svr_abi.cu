@@ -1,6 +1,7 @@
 // svr_abi.cu -- the C ABI of libsvr_b200.so (see include/svr_abi.h for the reference citations).
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <cfloat>
 #include <algorithm>
@@ -89,6 +90,8 @@ int svr_create(svr_context** out, int device)
     c->sm_count = prop.multiProcessorCount;
     SVR_CUDA(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    if (const char* e = getenv("SVR_TUNE_SCATTER")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->tune_scatter = v; }
+    if (const char* e = getenv("SVR_TUNE_SIMULATE")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->tune_simulate = v; }
     c->pinned_bytes = 4096;
     SVR_CUDA(nullptr, cudaMallocHost(&c->pinned, c->pinned_bytes));
     *out = c;
@@ -109,6 +112,7 @@ int svr_destroy(svr_context* c)
     dev_free(&c->mats); dev_free(&c->dims); dev_free(&c->partials);
     svr_reg_free(c);
     svr_pvr_free(c);
+    svr_window_free(c);
     prof_fold(c);
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->cub_tmp) cudaFree(c->cub_tmp);
@@ -134,6 +138,16 @@ int svr_synchronize(svr_context* c)
 }
 
 int64_t svr_launch_count(const svr_context* c) { return c ? c->launches : 0; }
+
+int svr_set_tuning(svr_context* c, int key, int value)
+{
+    REQUIRE(c, c, "null context");
+    switch (key) {
+    case SVR_TUNE_SCATTER: REQUIRE(c, value >= 0 && value <= 2, "svr_set_tuning: SVR_TUNE_SCATTER takes 0, 1 or 2"); c->tune_scatter = value; return 0;
+    case SVR_TUNE_SIMULATE: REQUIRE(c, value >= 0 && value <= 2, "svr_set_tuning: SVR_TUNE_SIMULATE takes 0, 1 or 2"); c->tune_simulate = value; return 0;
+    default: return fail_msg(c, "svr_set_tuning: unknown key");
+    }
+}
 
 int svr_profile_enable(svr_context* c, int on)
 {
@@ -191,6 +205,7 @@ int svr_init_reconstruction_volume(svr_context* c, int sx, int sy, int sz, float
     SVR_CUDA(c, cudaMemsetAsync(c->mask_f, 0, c->V * sizeof(float), c->stream));
     SVR_CUDA(c, cudaMemsetAsync(c->mask_u8, 0, c->V, c->stream));
     c->have_mask = false;
+    if (int r = svr_window_build_maps(c)) return r;      // tensor-map menus over acc2 / pack2 (svr_window.cu)
     if (data) return upload(c, c->recon, data, c->V * sizeof(float));
     SVR_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -262,7 +277,8 @@ int svr_fill_slices(svr_context* c, const float* cube, const int* sizesX, const 
     if (upload(c, c->slices, cube, c->NP * sizeof(float))) return 1;
     // "needed for stack-wise restore slice intensity" (cuda2.cu:1654-1655)
     SVR_CUDA(c, cudaMemcpyAsync(c->slices_restore, c->slices, c->NP * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-    return svr_launch_compact_valid(c);
+    if (int r = svr_launch_compact_valid(c)) return r;
+    return svr_window_build_tiles(c);
 }
 
 int svr_set_slice_dims(svr_context* c, const float* dims_xyz, float quality_factor)

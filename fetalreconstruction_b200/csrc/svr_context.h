@@ -42,6 +42,17 @@ struct svr_context {
     uint32_t n_valid = 0;
     uint32_t* pair_idx = nullptr;  // even-x pixels (x, x+1) of which at least one is != -1: the units of the paired scatter
     uint32_t n_pairs = 0;
+    // warp-window kernels (svr_window.cu): tiles of 8 x 4 pixels holding at least one pixel != -1, the dynamic tile queue,
+    // and the tensor-map menus (one CUtensorMap per window shape) over acc2 and pack2
+    uint32_t* tile_idx = nullptr;
+    size_t tile_cap = 0;
+    uint32_t n_tiles = 0;
+    int tilesX = 0, tilesPerSlice = 0;
+    unsigned int* ww_counter = nullptr;
+    void* maps_acc = nullptr;
+    void* maps_pack = nullptr;
+    int tune_scatter = 2;          // 0: paired scatter (round 1), 1: warp windows + SIMT flush, 2: warp windows + TMA reduce flush
+    int tune_simulate = 0;         // 0: per-tap loads (+ staged rows), 1: TMA-staged windows for every tile, 2: windows for through-plane slices only
     int* slice_count = nullptr;    // [S] per-slice voxel_num (deviation D4)
     int* slice_inside = nullptr;   // [S] OR of siminside since the last Gaussian reconstruction
     float* scales = nullptr;       // dev_d_scales: what the kernels see
@@ -126,3 +137,11 @@ int svr_launch_unpack_acc(svr_context* c);
 int svr_launch_equalize_inplace(svr_context* c);
 int svr_launch_deinterleave(svr_context* c, const float2* src, float* dst, int component);
 int svr_launch_flags_to_int(svr_context* c, const unsigned char* src, int* dst, size_t n);
+// svr_window.cu
+int svr_window_build_tiles(svr_context* c);
+int svr_window_build_maps(svr_context* c);
+void svr_window_free(svr_context* c);
+bool svr_window_scatter_available(const svr_context* c);
+bool svr_window_simulate_available(const svr_context* c);
+int svr_launch_window_scatter(svr_context* c, int mode);       // 0: K3, 1: K1 pass 2
+int svr_launch_window_simulate(svr_context* c, int only_class);

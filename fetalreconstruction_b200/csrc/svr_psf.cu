@@ -18,6 +18,7 @@
 //
 // Reference kernels restated here: reconstruction_cuda2.cu:176-295 (K1), 298-404 (K2), 408-522 (K3).
 #include "svr_context.h"
+#include "svr_psf_pixel.cuh"
 
 // Resident CTAs per SM the PSF kernels are compiled for (register budget = 65536 / (128 * SVR_MINB)).
 #ifndef SVR_MINB
@@ -92,29 +93,6 @@ int svr_launch_build_geom(svr_context* c)
                                                                  c->dims, ri2w, c->geom, c->flavor);
     SVR_KERNEL_CHECK(c);
     return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Flush one interior x-row of contributions p[0..15] (voxels v0 .. v0+15) scaled by (a, c) as paired
-// 128-bit reductions.  The pairs must be 16-byte aligned, so an odd v0 shifts the row by one voxel
-// (17 selects); the accumulator is allocated with 2 voxels of slack for the zero half of the last pair.
-template <int SUP>
-__device__ __forceinline__ void red_row_paired(float2* __restrict__ acc2, int v0, const float (&p)[SUP], float a, float c)
-{
-    const bool odd = (v0 & 1) != 0;
-    float4* base = reinterpret_cast<float4*>(acc2 + (v0 - (odd ? 1 : 0)));
-    float q[SUP + 2];
-    q[0] = odd ? 0.0f : p[0];
-#pragma unroll
-    for (int j = 1; j < SUP; ++j) q[j] = odd ? p[j - 1] : p[j];
-    q[SUP] = odd ? p[SUP - 1] : 0.0f;
-    q[SUP + 1] = 0.0f;
-#pragma unroll
-    for (int m = 0; m < SUP / 2 + 1; ++m) {
-        const float u = q[2 * m], w = q[2 * m + 1];
-        if (u + w > 0.0f)                                  // psf >= 0: skip all-zero pairs (and NaNs)
-            atomicAdd(base + m, make_float4(u * a, u * c, w * a, w * c));
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -275,47 +253,6 @@ gaussian_sume_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, i
     voxel_flag[idx] = 2;
 }
 
-// Pass 2 inputs of one pixel: false when pass 1 did not mark it.
-template <class TR>
-__device__ __forceinline__ bool gaussian_pixel(uint32_t idx, int Nx, int P, const float* __restrict__ slices,
-                                               const float* __restrict__ scales, const SliceGeom* __restrict__ geom,
-                                               const VolGeom& vg, const float* __restrict__ psf_sums,
-                                               const unsigned char* __restrict__ voxel_flag, int& k, PixelSetup& ps, float& sv, float& inv)
-{
-    if (voxel_flag[idx] != 2) return false;
-    k = idx / P;
-    const int pix = idx - k * P;
-    const int y = pix / Nx, x = pix - y * Nx;
-    ps = pixel_setup<TR>(geom[k], vg, x, y);
-    inv = 1.0f / psf_sums[idx];
-    sv = slices[idx] * scales[k] * inv;
-    return true;
-}
-
-template <class TR>
-__device__ __forceinline__ bool gaussian_single(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, float sv, float inv,
-                                                const unsigned char* __restrict__ mask, float2* __restrict__ acc2)
-{
-    bool any = false;
-    if (ps.interior) {
-        float p[TR::SUP];
-        auto tap = [&](int i, float psf, bool ok, int v) { p[i] = psf; if (ok && mask[v]) any = true; };
-        auto row = [&](int v0) { red_row_paired<TR::SUP>(acc2, v0, p, sv, inv); };
-        if (g.recur) psf_rows<TR, true, true>(g, vg, ps, tap, row);
-        else psf_rows<TR, true, false>(g, vg, ps, tap, row);
-    } else {
-        psf_rows_dispatch<TR>(g, vg, ps,
-            [&](int, float psf, bool ok, int v) {
-                if (ok) {
-                    atomicAdd(&acc2[v], make_float2(psf * sv, psf * inv));
-                    if (mask[v]) any = true;
-                }
-            },
-            [](int) {});
-    }
-    return any;
-}
-
 // Pass 2: one thread = one pixel pair (see scatter_pair).
 template <class TR>
 __global__ void __launch_bounds__(128, SVR_MINB_PAIR)
@@ -358,10 +295,12 @@ int svr_launch_gaussian_scatter(svr_context* c)
     if (c->n_valid == 0) return 0;
     ProfScope prof(c, 0);
     const int P = c->Nx * c->Ny;
+    const bool window = c->tune_scatter >= 1 && svr_window_scatter_available(c);
     if (c->flavor == 0) {
         gaussian_sume_kernel<SvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
             c->n_valid, c->valid_idx, c->Nx, P, c->geom, c->vg, c->psf_sums, c->voxel_flag, nullptr);
         SVR_KERNEL_CHECK(c);
+        if (window) return svr_launch_window_scatter(c, 1);
         gaussian_scatter_kernel<SvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
             c->n_pairs, c->pair_idx, c->Nx, P, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2, c->psf_sums,
             c->voxel_flag, c->slice_count);
@@ -369,6 +308,7 @@ int svr_launch_gaussian_scatter(svr_context* c)
         gaussian_sume_kernel<PvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
             c->n_valid, c->valid_idx, c->Nx, P, c->geom, c->vg, c->psf_sums, c->voxel_flag, c->use_spx ? c->spx : nullptr);
         SVR_KERNEL_CHECK(c);
+        if (window) return svr_launch_window_scatter(c, 1);
         gaussian_scatter_kernel<PvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
             c->n_pairs, c->pair_idx, c->Nx, P, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2, c->psf_sums,
             c->voxel_flag, c->slice_count);
@@ -444,12 +384,14 @@ __global__ void __launch_bounds__(128, SVR_MINB)
 simulate_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int Nx, int P,
                 const SliceGeom* __restrict__ geom, VolGeom vg, const float2* __restrict__ pack2,
                 const float* __restrict__ psf_sums, float* __restrict__ simslices, float* __restrict__ simweights,
-                unsigned char* __restrict__ siminside, int* __restrict__ slice_inside)
+                unsigned char* __restrict__ siminside, int* __restrict__ slice_inside, int skip_class)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t idx = 0;
     float sume = 0.0f;
     if (t < n_valid) { idx = valid_idx[t]; sume = psf_sums[idx]; }
+    // skip_class >= 0: slices with through_plane_rows == skip_class are left to the window kernel (svr_window.cu)
+    if (skip_class >= 0 && sume != 0.0f && geom[idx / P].through_plane_rows == skip_class) sume = 0.0f;
     const bool alive = sume != 0.0f;
 #if SVR_COOP
     if (TR::SUP != 16 && !alive) return;           // the cooperative path (SVR only) needs whole warps
@@ -503,58 +445,24 @@ int svr_launch_simulate(svr_context* c)
 {
     if (c->n_valid == 0) return 0;
     ProfScope prof(c, 1);
+    const int mode = svr_window_simulate_available(c) ? c->tune_simulate : 0;
+    if (mode == 1) return svr_launch_window_simulate(c, -1);
+    const int skip = mode == 2 ? 1 : -1;
     if (c->flavor == 0)
         simulate_kernel<SvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
             c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->geom, c->vg, c->pack2, c->psf_sums, c->simslices, c->simweights,
-            c->siminside, c->slice_inside);
+            c->siminside, c->slice_inside, skip);
     else
         simulate_kernel<PvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
             c->n_valid, c->valid_idx, c->Nx, c->Nx * c->Ny, c->geom, c->vg, c->pack2, c->psf_sums, c->simslices, c->simweights,
-            c->siminside, c->slice_inside);
+            c->siminside, c->slice_inside, skip);
     SVR_KERNEL_CHECK(c);
+    if (mode == 2) return svr_launch_window_simulate(c, 1);
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3: SuperresolutionKernel3D_tex (reconstruction_cuda2.cu:408-522).
-// Per-pixel inputs of K3: false when the pixel contributes nothing (no PSF mass or zero weight).
-template <class TR>
-__device__ __forceinline__ bool superres_pixel(uint32_t idx, int Nx, int P, const float* __restrict__ slices,
-                                               const float* __restrict__ weights, const float* __restrict__ simslices,
-                                               const float* __restrict__ slice_weights, const float* __restrict__ scales,
-                                               const float* __restrict__ psf_sums, int& k, int& x, int& y, float& aw, float& cw)
-{
-    const float sume = psf_sums[idx];
-    if (sume == 0.0f) return false;
-    k = idx / P;
-    const int pix = idx - k * P;
-    y = pix / Nx; x = pix - y * Nx;
-    const float w = weights[idx];
-    const float ss = simslices[idx];
-    float sliceVal = slices[idx] * scales[k];
-    sliceVal = (ss > 0.0f) ? (sliceVal - ss) : 0.0f;
-    cw = w * slice_weights[k] / sume;               // psf/sume * w * slice_weight
-    aw = cw * sliceVal;
-    return cw != 0.0f;                              // a pixel with zero weight adds exact zeros everywhere: skip its taps
-}
-
-template <class TR>
-__device__ __forceinline__ void superres_single(const SliceGeom& g, const VolGeom& vg, const PixelSetup& ps, float aw, float cw,
-                                                float2* __restrict__ acc2)
-{
-    if (ps.interior) {
-        float p[TR::SUP];
-        auto tap = [&](int i, float psf, bool, int) { p[i] = psf; };
-        auto row = [&](int v0) { red_row_paired<TR::SUP>(acc2, v0, p, aw, cw); };
-        if (g.recur) psf_rows<TR, true, true>(g, vg, ps, tap, row);
-        else psf_rows<TR, true, false>(g, vg, ps, tap, row);
-    } else {
-        psf_rows_dispatch<TR>(g, vg, ps,
-            [&](int, float psf, bool ok, int v) { if (ok) atomicAdd(&acc2[v], make_float2(psf * aw, psf * cw)); },
-            [](int) {});
-    }
-}
-
 // One thread = one pixel pair (see scatter_pair); pair_idx[t] = linear index of the pair's even-x pixel.
 template <class TR>
 __global__ void __launch_bounds__(128, SVR_MINB_PAIR)
@@ -595,6 +503,7 @@ int svr_launch_superres_scatter(svr_context* c)
 {
     if (c->n_pairs == 0) return 0;
     ProfScope prof(c, 2);
+    if (c->tune_scatter >= 1 && svr_window_scatter_available(c)) return svr_launch_window_scatter(c, 0);
     if (c->flavor == 0)
         superres_scatter_kernel<SvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
             c->n_pairs, c->pair_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,

@@ -72,6 +72,12 @@ class Reconstruction:
     def set_stream(self, cuda_stream_ptr: int | None):
         self._ck(self._lib.svr_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
+    TUNE_SCATTER, TUNE_SIMULATE = 0, 1
+
+    def set_tuning(self, key: int, value: int):
+        """Kernel-variant selection for A/B measurements (svr_set_tuning)."""
+        self._ck(self._lib.svr_set_tuning(self._h, int(key), int(value)))
+
     def synchronize(self):
         self._ck(self._lib.svr_synchronize(self._h))
 

@@ -48,6 +48,15 @@ int svr_set_stream(svr_context *ctx, void *cuda_stream);
 int svr_synchronize(svr_context *ctx);
 /* Number of kernels this context has launched since creation (for bench.py's gpu_launches). */
 int64_t svr_launch_count(const svr_context *ctx);
+/* Kernel-variant selection for A/B measurements (tools/, bench.py --tune); results agree within float summation order.
+ * No reference counterpart (the reference has compile-time switches only, .cuh:53-75). */
+enum {
+    SVR_TUNE_SCATTER = 0,   /* K1 pass 2 / K3: 0 = paired per-lane reductions, 1 = warp windows + SIMT flush,
+                               2 = warp windows + TMA reduce flush (default) */
+    SVR_TUNE_SIMULATE = 1   /* K2: 0 = per-tap loads + staged rows (default), 1 = TMA-staged windows for every tile,
+                               2 = windows for through-plane slices only */
+};
+int svr_set_tuning(svr_context *ctx, int key, int value);
 
 /* ---- uploads ---------------------------------------------------------------------------- */
 /* ref: InitReconstructionVolume(uint3 s, float3 dim, float* data, float sigma_bias) .cuh:230,
