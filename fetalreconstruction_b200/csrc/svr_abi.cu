@@ -90,7 +90,7 @@ int svr_create(svr_context** out, int device)
     c->sm_count = prop.multiProcessorCount;
     SVR_CUDA(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    if (const char* e = getenv("SVR_TUNE_SCATTER")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->tune_scatter = v; }
+    if (const char* e = getenv("SVR_TUNE_SCATTER")) { const int v = atoi(e); if (v >= 0 && v <= 3) c->tune_scatter = v; }
     if (const char* e = getenv("SVR_TUNE_SIMULATE")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->tune_simulate = v; }
     c->pinned_bytes = 4096;
     SVR_CUDA(nullptr, cudaMallocHost(&c->pinned, c->pinned_bytes));
@@ -143,7 +143,7 @@ int svr_set_tuning(svr_context* c, int key, int value)
 {
     REQUIRE(c, c, "null context");
     switch (key) {
-    case SVR_TUNE_SCATTER: REQUIRE(c, value >= 0 && value <= 2, "svr_set_tuning: SVR_TUNE_SCATTER takes 0, 1 or 2"); c->tune_scatter = value; return 0;
+    case SVR_TUNE_SCATTER: REQUIRE(c, value >= 0 && value <= 3, "svr_set_tuning: SVR_TUNE_SCATTER takes 0 .. 3"); c->tune_scatter = value; return 0;
     case SVR_TUNE_SIMULATE: REQUIRE(c, value >= 0 && value <= 2, "svr_set_tuning: SVR_TUNE_SIMULATE takes 0, 1 or 2"); c->tune_simulate = value; return 0;
     default: return fail_msg(c, "svr_set_tuning: unknown key");
     }
@@ -610,6 +610,9 @@ int svr_debug_get(svr_context* c, int kind, void* out)
         cudaFree(tmp);
         return rc;
     }
+    case SVR_DBG_WW_STATS:
+        if (!c->ww_counter) { memset(out, 0, 32 * sizeof(unsigned int)); return 0; }
+        return download(c, out, c->ww_counter + 8, 32 * sizeof(unsigned int));
     default: return fail_msg(c, "svr_debug_get: unknown kind");
     }
 }

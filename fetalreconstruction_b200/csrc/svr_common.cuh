@@ -47,6 +47,8 @@ struct __align__(16) SliceGeom {
     int recur;                   // 1 when the recurrence cannot overflow (|bz0| <= 1, |bz0|+|bz1|+|bz2| <= 4)
     int through_plane_rows;      // 1 when a step along the slice's x moves less than half a voxel along the volume's x:
                                  // the tap rows (runs along volume x) of a warp's pixels then share no cache lines
+    int win_class;               // 1: the slice's x / y axes are not both within ~10 degrees of the volume's x / y axes: its scatter
+                                 // goes through the warp-window kernel under SVR_TUNE_SCATTER = 3 (svr_window.cu)
 };
 
 struct VolGeom {

@@ -51,7 +51,8 @@ struct svr_context {
     unsigned int* ww_counter = nullptr;
     void* maps_acc = nullptr;
     void* maps_pack = nullptr;
-    int tune_scatter = 2;          // 0: paired scatter (round 1), 1: warp windows + SIMT flush, 2: warp windows + TMA reduce flush
+    int tune_scatter = 0;          // 0: paired scatter (round 1), 1: warp windows + SIMT flush, 2: warp windows + TMA reduce flush,
+                                   // 3: paired for slices aligned with the volume axes, warp windows (TMA flush) for the others
     int tune_simulate = 0;         // 0: per-tap loads (+ staged rows), 1: TMA-staged windows for every tile, 2: windows for through-plane slices only
     int* slice_count = nullptr;    // [S] per-slice voxel_num (deviation D4)
     int* slice_inside = nullptr;   // [S] OR of siminside since the last Gaussian reconstruction
@@ -143,5 +144,5 @@ int svr_window_build_maps(svr_context* c);
 void svr_window_free(svr_context* c);
 bool svr_window_scatter_available(const svr_context* c);
 bool svr_window_simulate_available(const svr_context* c);
-int svr_launch_window_scatter(svr_context* c, int mode);       // 0: K3, 1: K1 pass 2
+int svr_launch_window_scatter(svr_context* c, int mode, int only_class);   // mode 0: K3, 1: K1 pass 2; only_class -1: all slices
 int svr_launch_window_simulate(svr_context* c, int only_class);

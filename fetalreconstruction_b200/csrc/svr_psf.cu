@@ -79,6 +79,8 @@ __global__ void build_geom_kernel(int S, const float* __restrict__ T, const floa
         // direction of a slice-x step in voxel space
         const float nx = sqrtf(comb[0] * comb[0] + comb[1] * comb[1] + comb[2] * comb[2]);
         g.through_plane_rows = (nx > 0.f && fabsf(comb[0]) < 0.5f * nx) ? 1 : 0;
+        const float ny = sqrtf(comb[4] * comb[4] + comb[5] * comb[5] + comb[6] * comb[6]);
+        g.win_class = (fabsf(comb[0]) > 0.985f * nx && fabsf(comb[5]) > 0.985f * ny) ? 0 : 1;
     }
     out[k] = g;
 }
@@ -260,11 +262,12 @@ gaussian_scatter_kernel(uint32_t n_pairs, const uint32_t* __restrict__ pair_idx,
                         const float* __restrict__ slices, const float* __restrict__ scales,
                         const SliceGeom* __restrict__ geom, VolGeom vg, const unsigned char* __restrict__ mask,
                         float2* __restrict__ acc2, const float* __restrict__ psf_sums, unsigned char* __restrict__ voxel_flag,
-                        int* __restrict__ slice_count)
+                        int* __restrict__ slice_count, int skip_win)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_pairs) return;
     const uint32_t ia = pair_idx[t];
+    if (skip_win && geom[ia / (uint32_t)P].win_class) return;      // left to the warp-window kernel
     const int xe = (int)(ia % (uint32_t)Nx);
     int k = 0, kB = 0;
     PixelSetup psA = {}, psB = {};
@@ -295,25 +298,28 @@ int svr_launch_gaussian_scatter(svr_context* c)
     if (c->n_valid == 0) return 0;
     ProfScope prof(c, 0);
     const int P = c->Nx * c->Ny;
-    const bool window = c->tune_scatter >= 1 && svr_window_scatter_available(c);
+    const bool avail = svr_window_scatter_available(c);
+    const bool window = (c->tune_scatter == 1 || c->tune_scatter == 2) && avail;
+    const int split = (c->tune_scatter == 3 && avail) ? 1 : 0;     // aligned slices: paired scatter, the others: warp windows
     if (c->flavor == 0) {
         gaussian_sume_kernel<SvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
             c->n_valid, c->valid_idx, c->Nx, P, c->geom, c->vg, c->psf_sums, c->voxel_flag, nullptr);
         SVR_KERNEL_CHECK(c);
-        if (window) return svr_launch_window_scatter(c, 1);
+        if (window) return svr_launch_window_scatter(c, 1, -1);
         gaussian_scatter_kernel<SvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
             c->n_pairs, c->pair_idx, c->Nx, P, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2, c->psf_sums,
-            c->voxel_flag, c->slice_count);
+            c->voxel_flag, c->slice_count, split);
     } else {
         gaussian_sume_kernel<PvrTraits><<<divup_i(c->n_valid, 128), 128, 0, c->stream>>>(
             c->n_valid, c->valid_idx, c->Nx, P, c->geom, c->vg, c->psf_sums, c->voxel_flag, c->use_spx ? c->spx : nullptr);
         SVR_KERNEL_CHECK(c);
-        if (window) return svr_launch_window_scatter(c, 1);
+        if (window) return svr_launch_window_scatter(c, 1, -1);
         gaussian_scatter_kernel<PvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
             c->n_pairs, c->pair_idx, c->Nx, P, c->slices, c->scales, c->geom, c->vg, c->mask_u8, c->acc2, c->psf_sums,
-            c->voxel_flag, c->slice_count);
+            c->voxel_flag, c->slice_count, split);
     }
     SVR_KERNEL_CHECK(c);
+    if (split) return svr_launch_window_scatter(c, 1, 1);
     return 0;
 }
 
@@ -470,11 +476,12 @@ superres_scatter_kernel(uint32_t n_pairs, const uint32_t* __restrict__ pair_idx,
                         const float* __restrict__ slices, const float* __restrict__ weights,
                         const float* __restrict__ simslices, const float* __restrict__ slice_weights,
                         const float* __restrict__ scales, const SliceGeom* __restrict__ geom, VolGeom vg,
-                        const float* __restrict__ psf_sums, float2* __restrict__ acc2)
+                        const float* __restrict__ psf_sums, float2* __restrict__ acc2, int skip_win)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_pairs) return;
     const uint32_t ia = pair_idx[t];
+    if (skip_win && geom[ia / (uint32_t)P].win_class) return;      // left to the warp-window kernel
     int k = 0, xA = 0, yA = 0, kB = 0, xB = 0, yB = 0;
     float awA = 0.f, cwA = 0.f, awB = 0.f, cwB = 0.f;
     const int xe = (int)(ia % (uint32_t)Nx);
@@ -503,16 +510,19 @@ int svr_launch_superres_scatter(svr_context* c)
 {
     if (c->n_pairs == 0) return 0;
     ProfScope prof(c, 2);
-    if (c->tune_scatter >= 1 && svr_window_scatter_available(c)) return svr_launch_window_scatter(c, 0);
+    const bool avail = svr_window_scatter_available(c);
+    if ((c->tune_scatter == 1 || c->tune_scatter == 2) && avail) return svr_launch_window_scatter(c, 0, -1);
+    const int split = (c->tune_scatter == 3 && avail) ? 1 : 0;
     if (c->flavor == 0)
         superres_scatter_kernel<SvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
             c->n_pairs, c->pair_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
-            c->geom, c->vg, c->psf_sums, c->acc2);
+            c->geom, c->vg, c->psf_sums, c->acc2, split);
     else
         superres_scatter_kernel<PvrTraits><<<divup_i(c->n_pairs, 128), 128, 0, c->stream>>>(
             c->n_pairs, c->pair_idx, c->Nx, c->Nx * c->Ny, c->slices, c->weights, c->simslices, c->slice_weights, c->scales,
-            c->geom, c->vg, c->psf_sums, c->acc2);
+            c->geom, c->vg, c->psf_sums, c->acc2, split);
     SVR_KERNEL_CHECK(c);
+    if (split) return svr_launch_window_scatter(c, 0, 1);
     return 0;
 }
 

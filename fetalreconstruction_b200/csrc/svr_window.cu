@@ -39,63 +39,107 @@ constexpr int WW_WARPS = 4;                  // warps per CTA (independent: no C
 constexpr int WW_WIN_VOX = 1536;             // float2 voxels of window per warp (12 KB)
 constexpr int WW_SMEM = WW_WARPS * WW_WIN_VOX * 8 + WW_WARPS * 8;     // windows + one mbarrier per warp
 
-// Window dimensions are quantised so that a fixed menu of TMA tensor maps (box shape = window shape) covers them.
-constexpr int WW_NQX = 10, WW_NQ = 19;
-__host__ __device__ __forceinline__ int ww_qx_val(int i)
+// Window layout.  A window holds nz planes of ny rows of the volume; voxel (x, y, z) relative to the window origin lives
+// at float2 index x + RS * y + PS * z.  The strides are padded per tile so that the 16 lanes of a half-warp (one
+// shared-memory phase of a 64-bit access) fall into different 8-byte bank pairs: every tap instruction of the scatter is
+// a read-modify-write of 512 B per warp, i.e. the shared-memory pipe is ~60 % busy when conflict-free and the bound of
+// the kernel as soon as it is not (measured: oblique stacks at 3-4 way conflicts ran 1.7x slower than aligned ones).
+// TMA-compatible layouts are dense boxes (RS even, PS = RS * by) drawn from a menu of tensor maps, one per box shape.
+constexpr int WW_MENU_X0 = 12, WW_MENU_NX = 23;     // box widths 12, 14, ..., 56 voxels
+constexpr int WW_MENU_N = 32;                       // box heights / depths 1 .. 32
+__host__ __device__ __forceinline__ int ww_menu_index(int rs, int by, int bz)
 {
-    return i <= 5 ? 18 + 2 * i : (i == 6 ? 32 : (i == 7 ? 36 : (i == 8 ? 40 : 48)));
-}
-__host__ __device__ __forceinline__ int ww_q_val(int i) { return i < 8 ? i + 1 : (i < 18 ? 10 + 2 * (i - 8) : 32); }
-__device__ __forceinline__ int ww_qx_idx(int n)
-{   // smallest menu entry >= n, -1 when none
-    if (n <= 18) return 0;
-    if (n <= 28) return (n - 18 + 1) >> 1;
-    if (n <= 32) return 6;
-    if (n <= 36) return 7;
-    if (n <= 40) return 8;
-    if (n <= 48) return 9;
-    return -1;
-}
-__device__ __forceinline__ int ww_q_idx(int n)
-{
-    if (n <= 8) return n - 1;
-    if (n <= 28) return 8 + ((n - 10 + 1) >> 1);
-    if (n <= 32) return 18;
-    return -1;
+    return (((rs - WW_MENU_X0) >> 1) * WW_MENU_N + (by - 1)) * WW_MENU_N + (bz - 1);
 }
 
 struct WinPlan {
     int S;                 // inner steps per flush (0: no window)
     int inner_z;           // 1: z is the inner tap-row axis, 0: y
-    int bx, by, bz;        // window layout (voxels): row stride, rows per plane, planes
-    int map;               // index into the tensor-map menu
+    int RS, PS;            // row / plane stride (voxels)
+    int nx, ny, nz;        // used extent (voxels): nx <= RS, ny * RS <= PS
+    int tma;               // 1: dense box from the menu (PS = RS * by): the TMA unit can move it
+    int map;               // menu index when tma
+    int deg;               // bank-conflict degree of the layout (1 = conflict-free)
 };
 
-// ex, ey, ez: extents of the tile's centre voxels; need_x = ex + SUP - 1 (+1 when the origin was rounded down to even).
-__device__ __forceinline__ WinPlan ww_plan(int need_x, int ey, int ez, int SUP)
+// Conflict degree of a layout: the largest number of lanes of one half-warp whose tap-0 address falls into the same
+// bank pair.  (lx, ly, lz) = the lane's centre voxel relative to the tile's bounding box; the inner step and the tap index
+// shift every lane's address by the same amount, so this is the degree of every tap instruction of the tile.
+__device__ __forceinline__ int ww_conflict(bool use, int lx, int ly, int lz, int RS, int PS, int lane)
 {
-    WinPlan w; w.S = 0; w.inner_z = 0; w.bx = w.by = w.bz = 0; w.map = 0;
-    const int ix = ww_qx_idx(need_x);
-    if (ix < 0) return w;
-    const int bx = ww_qx_val(ix);
+    const unsigned b = (unsigned)(lx + RS * ly + PS * lz) & 15u;
+    const unsigned key = use ? (b | ((unsigned)(lane >> 4) << 4)) : (64u + (unsigned)lane);
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    return __reduce_max_sync(0xffffffffu, use ? __popc(grp) : 1);
+}
+
+// need_x: voxels per window row; ey, ez: extents of the tile's centre voxels.  want: 0 = any layout, 1 = TMA layouts only,
+// 2 = TMA unless a general layout has fewer conflicts.
+__device__ __forceinline__ WinPlan ww_plan(int need_x, int ey, int ez, int SUP, int want, bool use, int lx, int ly, int lz, int lane)
+{
+    WinPlan w; w.S = 0; w.inner_z = 0; w.RS = w.PS = 0; w.nx = need_x; w.ny = w.nz = 0; w.tma = 0; w.map = 0; w.deg = 0;
+    const int nxe = (need_x + 1) & ~1;
     for (int S = SUP; S >= 1; S >>= 1) {
-        const int iyY = ww_q_idx(ey + S - 1), izY = ww_q_idx(ez);         // inner = y
-        const int iyZ = ww_q_idx(ey), izZ = ww_q_idx(ez + S - 1);         // inner = z
-        const int volY = (iyY < 0 || izY < 0) ? (1 << 30) : bx * ww_q_val(iyY) * ww_q_val(izY);
-        const int volZ = (iyZ < 0 || izZ < 0) ? (1 << 30) : bx * ww_q_val(iyZ) * ww_q_val(izZ);
+        const int volY = nxe * (ey + S - 1) * ez, volZ = nxe * ey * (ez + S - 1);
         const bool z = volZ < volY;
-        const int vol = z ? volZ : volY;
-        if (vol <= WW_WIN_VOX) {
-            const int iy = z ? iyZ : iyY, iz = z ? izZ : izY;
-            w.S = S; w.inner_z = z ? 1 : 0; w.bx = bx; w.by = ww_q_val(iy); w.bz = ww_q_val(iz);
-            w.map = (ix * WW_NQ + iy) * WW_NQ + iz;
+        if ((z ? volZ : volY) > WW_WIN_VOX) continue;
+        w.S = S; w.inner_z = z ? 1 : 0;
+        w.ny = z ? ey : ey + S - 1;
+        w.nz = z ? ez + S - 1 : ez;
+        break;
+    }
+    if (w.S == 0) return w;
+    int best = 99;
+    if (want >= 1 && w.nz <= WW_MENU_N) {          // dense boxes: widths nxe + 2k, heights ny + j
+        for (int k = 0; k < 4 && best > 1; ++k) {
+            const int RS = nxe + 2 * k;
+            if (RS < WW_MENU_X0 || RS > WW_MENU_X0 + 2 * (WW_MENU_NX - 1)) continue;
+            for (int j = 0; j < 4 && best > 1; ++j) {
+                const int by = w.ny + j;
+                if (by > WW_MENU_N || RS * by * w.nz > WW_WIN_VOX) break;
+                const int d = ww_conflict(use, lx, ly, lz, RS, RS * by, lane);
+                if (d < best) { best = d; w.RS = RS; w.PS = RS * by; w.tma = 1; w.map = ww_menu_index(RS, by, w.nz); }
+            }
+        }
+        if (want == 1 || best <= 1) {
+            if (best == 99) w.S = 0;
+            w.deg = best;
             return w;
         }
     }
+    for (int dr = 0; dr < 8 && best > 1; ++dr) {    // general strides
+        const int RS = need_x + dr;
+        for (int dp = 0; dp < 16 && best > 1; ++dp) {
+            const int PS = RS * w.ny + dp;
+            if (PS * w.nz > WW_WIN_VOX) break;
+            const int d = ww_conflict(use, lx, ly, lz, RS, PS, lane);
+            if (d < best) { best = d; w.RS = RS; w.PS = PS; w.tma = 0; }
+        }
+    }
+    if (best == 99) w.S = 0;
+    w.deg = best;
     return w;
 }
 
+// Plan statistics (svr_debug_get SVR_DBG_WW_STATS): [0..4] tiles by log2(S) (S = 1, 2, 4, 8, 16; S = 12, 6, 3 of the 12^3
+// support count as 8, 4, 2), [5] tiles without a window, [8..15] tiles by conflict degree 1 .. 8+, [16] TMA layouts,
+// [17] general layouts, [18] tiles with lanes sharing a centre voxel, [19] one-pixel fallbacks (pixels).
+__device__ __forceinline__ void ww_count(unsigned int* stats, const WinPlan& w, int nrounds, int fallback_px, int lane)
+{
+    if (!stats || lane != 0) return;
+    if (w.S == 0) atomicAdd(stats + 5, 1u);
+    else {
+        atomicAdd(stats + (31 - __clz(w.S)), 1u);
+        atomicAdd(stats + 8 + min(max(w.deg, 1), 8) - 1, 1u);
+        atomicAdd(stats + (w.tma ? 16 : 17), 1u);
+        if (nrounds > 1) atomicAdd(stats + 18, 1u);
+    }
+    if (fallback_px) atomicAdd(stats + 19, (unsigned)fallback_px);
+}
+
 __device__ __forceinline__ uint32_t ww_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t ww_magic(int d) { return d > 1 ? 0xffffffffu / (uint32_t)d + 1u : 0u; }   // q / d = umulhi(q, magic), q < 2^16
+__device__ __forceinline__ int ww_div(int q, int d, uint32_t m) { return d > 1 ? (int)__umulhi((uint32_t)q, m) : q; }
 
 // ---------------------------------------------------------------------------------------------
 // Window -> accumulator.
@@ -113,31 +157,44 @@ __device__ __forceinline__ void ww_flush_tma(float2* win, const WinPlan& w, cons
     }
     __syncwarp();
     float4* w4 = reinterpret_cast<float4*>(win);
-    const int n4 = (w.bx * w.by * w.bz) >> 1;
+    const int n4 = (w.PS * w.nz + 1) >> 1;
     for (int q = lane; q < n4; q += 32) w4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 }
 
-// SIMT form: consecutive lanes read consecutive 16-byte chunks (two voxels) of the window, clear them and send the
-// non-zero ones as 128-bit reductions.  used_z planes of by rows each carry data.
+// SIMT form: consecutive lanes read consecutive pieces of the used part of the window, clear them and send the non-zero
+// ones as vector reductions: 16-byte pieces (two voxels) when the strides keep every row 16-byte aligned, 8-byte otherwise.
 __device__ __forceinline__ void ww_flush_simt(float2* win, const WinPlan& w, float2* __restrict__ acc2, int vx, int vy,
-                                              int X0, int Y0, int Z0, int used_z, int lane)
+                                              int X0, int Y0, int Z0, int lane)
 {
     __syncwarp();
-    float4* w4 = reinterpret_cast<float4*>(win);
-    const int hb = w.bx >> 1;
-    const int n4 = hb * w.by * used_z;
-    const uint32_t m_hb = 0xffffffffu / (uint32_t)hb + 1u, m_by = 0xffffffffu / (uint32_t)w.by + 1u;   // exact for q < 2^16
-    for (int q = lane; q < n4; q += 32) {
-        const float4 v = w4[q];
-        if (v.y + v.w > 0.0f) {                          // denominators are sums of psf * c with c > 0
-            w4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int row = (int)__umulhi((uint32_t)q, m_hb), ch = q - row * hb;
-            const int wz = (int)__umulhi((uint32_t)row, m_by), wy = row - wz * w.by;
-            float4* dst = reinterpret_cast<float4*>(acc2 + ((size_t)((Z0 + wz) * vy + (Y0 + wy)) * vx + X0)) + ch;
-            atomicAdd(dst, v);
-        } else if (v.x != 0.0f || v.z != 0.0f || v.y != 0.0f || v.w != 0.0f) {
-            w4[q] = make_float4(0.f, 0.f, 0.f, 0.f);     // NaN / non-positive denominators are dropped like red_row_paired does
+    if (((w.RS | w.PS) & 1) == 0) {
+        const int hx = (w.nx + 1) >> 1;
+        const int n = hx * w.ny * w.nz;
+        const uint32_t m_hx = ww_magic(hx), m_ny = ww_magic(w.ny);
+        for (int q = lane; q < n; q += 32) {
+            const int row = ww_div(q, hx, m_hx), ch = q - row * hx;
+            const int wz = ww_div(row, w.ny, m_ny), wy = row - wz * w.ny;
+            float4* src = reinterpret_cast<float4*>(win + wz * w.PS + wy * w.RS) + ch;
+            const float4 v = *src;
+            if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) {
+                *src = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v.y + v.w > 0.0f)                      // denominators are sums of psf * c, c > 0 (NaNs are dropped, as red_row_paired does)
+                    atomicAdd(reinterpret_cast<float4*>(acc2 + ((size_t)((Z0 + wz) * vy + (Y0 + wy)) * vx + X0)) + ch, v);
+            }
+        }
+    } else {
+        const int n = w.nx * w.ny * w.nz;
+        const uint32_t m_nx = ww_magic(w.nx), m_ny = ww_magic(w.ny);
+        for (int q = lane; q < n; q += 32) {
+            const int row = ww_div(q, w.nx, m_nx), x = q - row * w.nx;
+            const int wz = ww_div(row, w.ny, m_ny), wy = row - wz * w.ny;
+            float2* src = win + wz * w.PS + wy * w.RS + x;
+            const float2 v = *src;
+            if (v.x != 0.0f || v.y != 0.0f) {
+                *src = make_float2(0.f, 0.f);
+                if (v.y > 0.0f) atomicAdd(acc2 + ((size_t)((Z0 + wz) * vy + (Y0 + wy)) * vx + X0 + x), v);
+            }
         }
     }
     __syncwarp();
@@ -157,6 +214,8 @@ struct WWScatterArgs {
     int* slice_count;
     const CUtensorMap* maps;           // menu over acc2 (nullptr: SIMT flush only)
     int flush_tma;
+    int only_class;                    // -1: every tile, else only tiles of slices with win_class == only_class
+    unsigned int* stats;               // plan statistics (may be nullptr)
 };
 
 // One tile.  MODE 0: K3 (superresolution), MODE 1: K1 pass 2 (Gaussian reconstruction, with the per-pixel mask flag).
@@ -195,9 +254,14 @@ __device__ __forceinline__ void ww_scatter_tile(const WWScatterArgs& a, const Vo
         const int y1 = __reduce_max_sync(FULL, use ? ps.cy : -0x7fffffff);
         const int z1 = __reduce_max_sync(FULL, use ? ps.cz : -0x7fffffff);
         X0 = (x0 - CEN) & ~1;                                // even: 16-byte aligned rows in the accumulator (vx is even)
-        w = ww_plan(x1 + (SUP - 1 - CEN) - X0 + 1, y1 - y0 + 1, z1 - z0 + 1, SUP);
+        w = ww_plan(x1 + (SUP - 1 - CEN) - X0 + 1, y1 - y0 + 1, z1 - z0 + 1, SUP, a.flush_tma ? 2 : 0, use,
+                    ps.cx - CEN - X0, ps.cy - y0, ps.cz - z0, lane);
     }
     if (w.S == 0) use = false;
+    {
+        const unsigned fb = __ballot_sync(FULL, live && !use);
+        if (usemask || fb) ww_count(a.stats, w, 1, __popc(fb), lane);
+    }
     if (live && !use) {
         if (MODE == 0) superres_single<TR>(g, vg, ps, aw, cw, a.acc2);
         else any = gaussian_single<TR>(g, vg, ps, aw, cw, a.mask, a.acc2);
@@ -208,6 +272,7 @@ __device__ __forceinline__ void ww_scatter_tile(const WWScatterArgs& a, const Vo
         const unsigned grp = __match_any_sync(FULL, key);
         const int rank = __popc(grp & ((1u << lane) - 1u));
         const int nrounds = __reduce_max_sync(FULL, rank) + 1;
+        if (nrounds > 1 && a.stats && lane == 0) atomicAdd(a.stats + 18, 1u);
         const int vx = vg.vx, vy = vg.vy;
         if (MODE == 1 && use) {
             // the row through the pixel's own centre voxel almost always decides the mask flag (see scatter_pair)
@@ -217,26 +282,26 @@ __device__ __forceinline__ void ww_scatter_tile(const WWScatterArgs& a, const Vo
 #pragma unroll
             for (int i = 0; i < SUP; ++i) if (p[i] != 0.0f && a.mask[v0 + i]) any = true;
         }
-        // outer / inner tap-row axes
-        const float bOx = w.inner_z ? g.bx[1] : g.bx[2], bOy = w.inner_z ? g.by[1] : g.by[2], bOz = w.inner_z ? g.bz[1] : g.bz[2];
-        const float bIx = w.inner_z ? g.bx[2] : g.bx[1], bIy = w.inner_z ? g.by[2] : g.by[1], bIz = w.inner_z ? g.bz[2] : g.bz[1];
-        const int strideI = w.inner_z ? w.by * w.bx : w.bx;
-        const int lane_base = ((ps.cz - z0) * w.by + (ps.cy - y0)) * w.bx + (ps.cx - CEN - X0);
+        const float bx1 = g.bx[1], by1 = g.by[1], bz1 = g.bz[1];
+        const float bx2 = g.bx[2], by2 = g.by[2], bz2 = g.bz[2];
+        const int strideI = w.inner_z ? w.PS : w.RS;
+        const int lane_base = (ps.cz - z0) * w.PS + (ps.cy - y0) * w.RS + (ps.cx - CEN - X0);
 #pragma unroll 1
         for (int o = 0; o < SUP; ++o) {
-            const float fo = (float)(o - CEN);
-            const float ox = fmaf(fo, bOx, ps.ex), oy = fmaf(fo, bOy, ps.ey), oz = fmaf(fo, bOz, ps.ez);
 #pragma unroll 1
             for (int c0 = 0; c0 < SUP; c0 += w.S) {
 #pragma unroll 1
                 for (int s = 0; s < w.S; ++s) {
-                    const float fi = (float)(c0 + s - CEN);
+                    const int oy = (w.inner_z ? o : c0 + s) - CEN, oz = (w.inner_z ? c0 + s : o) - CEN;
                     float p[SUP];
                     if (use) {
-                        psf_row_values<TR, RECUR>(g, fmaf(fi, bIx, ox), fmaf(fi, bIy, oy), fmaf(fi, bIz, oz), p);
+                        // tap-row position in the operation order of psf_rows (z term first): the tap values, and with them the
+                        // epsilon-skip decisions, are bit-identical to those of the other PSF kernels whatever the loop order
+                        const float foz = (float)oz, foy = (float)oy;
+                        const float zx = fmaf(foz, bx2, ps.ex), zy = fmaf(foz, by2, ps.ey), zz = fmaf(foz, bz2, ps.ez);
+                        psf_row_values<TR, RECUR>(g, fmaf(foy, bx1, zx), fmaf(foy, by1, zy), fmaf(foy, bz1, zz), p);
                         if (MODE == 1 && !any) {
-                            const int yy = ps.cy + (w.inner_z ? o : c0 + s) - CEN, zz = ps.cz + (w.inner_z ? c0 + s : o) - CEN;
-                            const int v0 = (zz * vy + yy) * vx + ps.cx - CEN;
+                            const int v0 = ((ps.cz + oz) * vy + ps.cy + oy) * vx + ps.cx - CEN;
 #pragma unroll
                             for (int i = 0; i < SUP; ++i) if (p[i] != 0.0f && a.mask[v0 + i]) any = true;
                         }
@@ -263,8 +328,8 @@ __device__ __forceinline__ void ww_scatter_tile(const WWScatterArgs& a, const Vo
                 // window origin in the volume for this (outer offset, chunk)
                 const int Y0 = w.inner_z ? y0 + o - CEN : y0 - CEN + c0;
                 const int Z0 = w.inner_z ? z0 - CEN + c0 : z0 + o - CEN;
-                if (a.flush_tma) ww_flush_tma(win, w, a.maps, X0, Y0, Z0, lane);
-                else ww_flush_simt(win, w, a.acc2, vx, vy, X0, Y0, Z0, w.bz, lane);
+                if (w.tma) ww_flush_tma(win, w, a.maps, X0, Y0, Z0, lane);
+                else ww_flush_simt(win, w, a.acc2, vx, vy, X0, Y0, Z0, lane);
             }
         }
     }
@@ -303,6 +368,7 @@ window_scatter_kernel(const __grid_constant__ WWScatterArgs a, const __grid_cons
         const int x = tx * WW_TW + (lane & (WW_TW - 1)), y = ty * WW_TH + (lane / WW_TW);
         const bool inb = x < a.Nx && y < a.Ny;
         const SliceGeom& g = a.geom[k];
+        if (a.only_class >= 0 && g.win_class != a.only_class) continue;
         if (g.recur) ww_scatter_tile<TR, MODE, true>(a, vg, g, k, x, y, inb, win, lane);
         else ww_scatter_tile<TR, MODE, false>(a, vg, g, k, x, y, inb, win, lane);
     }
@@ -349,7 +415,7 @@ __device__ __forceinline__ void ww_simulate_tile(const WWSimArgs& a, const VolGe
         const int y1 = __reduce_max_sync(FULL, use ? ps.cy : -0x7fffffff);
         const int z1 = __reduce_max_sync(FULL, use ? ps.cz : -0x7fffffff);
         X0 = (x0 - CEN) & ~1;
-        w = ww_plan(x1 + (SUP - 1 - CEN) - X0 + 1, y1 - y0 + 1, z1 - z0 + 1, SUP);
+        w = ww_plan(x1 + (SUP - 1 - CEN) - X0 + 1, y1 - y0 + 1, z1 - z0 + 1, SUP, 1, use, ps.cx - CEN - X0, ps.cy - y0, ps.cz - z0, lane);
     }
     if (w.S == 0) use = false;
     float sim = 0.f, wsum = 0.f;
@@ -364,15 +430,13 @@ __device__ __forceinline__ void ww_simulate_tile(const WWSimArgs& a, const VolGe
         psf_rows_dispatch<TR>(g, vg, ps, tap, [](int) {});
     }
     if (w.S != 0) {
-        const float bOx = w.inner_z ? g.bx[1] : g.bx[2], bOy = w.inner_z ? g.by[1] : g.by[2], bOz = w.inner_z ? g.bz[1] : g.bz[2];
-        const float bIx = w.inner_z ? g.bx[2] : g.bx[1], bIy = w.inner_z ? g.by[2] : g.by[1], bIz = w.inner_z ? g.bz[2] : g.bz[1];
-        const int strideI = w.inner_z ? w.by * w.bx : w.bx;
-        const int lane_base = ((ps.cz - z0) * w.by + (ps.cy - y0)) * w.bx + (ps.cx - CEN - X0);
-        const uint32_t bytes = (uint32_t)(w.bx * w.by * w.bz) * 8u;
+        const float bx1 = g.bx[1], by1 = g.by[1], bz1 = g.bz[1];
+        const float bx2 = g.bx[2], by2 = g.by[2], bz2 = g.bz[2];
+        const int strideI = w.inner_z ? w.PS : w.RS;
+        const int lane_base = (ps.cz - z0) * w.PS + (ps.cy - y0) * w.RS + (ps.cx - CEN - X0);
+        const uint32_t bytes = (uint32_t)(w.PS * w.nz) * 8u;
 #pragma unroll 1
         for (int o = 0; o < SUP; ++o) {
-            const float fo = (float)(o - CEN);
-            const float ox = fmaf(fo, bOx, ps.ex), oy = fmaf(fo, bOy, ps.ey), oz = fmaf(fo, bOz, ps.ez);
 #pragma unroll 1
             for (int c0 = 0; c0 < SUP; c0 += w.S) {
                 const int Y0 = w.inner_z ? y0 + o - CEN : y0 - CEN + c0;
@@ -393,9 +457,11 @@ __device__ __forceinline__ void ww_simulate_tile(const WWSimArgs& a, const VolGe
                 if (use) {
 #pragma unroll 1
                     for (int s = 0; s < w.S; ++s) {
-                        const float fi = (float)(c0 + s - CEN);
+                        const int oy = (w.inner_z ? o : c0 + s) - CEN, oz = (w.inner_z ? c0 + s : o) - CEN;
+                        const float foz = (float)oz, foy = (float)oy;
+                        const float zx = fmaf(foz, bx2, ps.ex), zy = fmaf(foz, by2, ps.ey), zz = fmaf(foz, bz2, ps.ez);
                         float p[SUP];
-                        psf_row_values<TR, RECUR>(g, fmaf(fi, bIx, ox), fmaf(fi, bIy, oy), fmaf(fi, bIz, oz), p);
+                        psf_row_values<TR, RECUR>(g, fmaf(foy, bx1, zx), fmaf(foy, by1, zy), fmaf(foy, bz1, zz), p);
                         const float2* wp = win + lane_base + s * strideI;
 #pragma unroll
                         for (int i = 0; i < SUP; ++i) {
@@ -487,7 +553,10 @@ int svr_window_build_tiles(svr_context* c)
         SVR_CUDA(c, cudaMalloc(&c->tile_idx, n * sizeof(uint32_t)));
         c->tile_cap = n;
     }
-    if (!c->ww_counter) SVR_CUDA(c, cudaMalloc(&c->ww_counter, sizeof(unsigned int)));
+    if (!c->ww_counter) {
+        SVR_CUDA(c, cudaMalloc(&c->ww_counter, 40 * sizeof(unsigned int)));      // [0] tile queue, [8..39] plan statistics of the last scatter
+        SVR_CUDA(c, cudaMemsetAsync(c->ww_counter, 0, 40 * sizeof(unsigned int), c->stream));
+    }
     thrust::counting_iterator<uint32_t> it(0);
     TileHead pred{ c->slices, c->Nx, c->Ny, c->tilesX, c->tilesPerSlice, c->Nx * c->Ny };
     int* d_num = (int*)(c->partials);
@@ -533,19 +602,19 @@ static int build_menu(svr_context* c, void* base, CUtensorMap** dev_menu)
         if (*dev_menu) { cudaFree(*dev_menu); *dev_menu = nullptr; }
         return 0;
     }
-    const int n = WW_NQX * WW_NQ * WW_NQ;
+    const int n = WW_MENU_NX * WW_MENU_N * WW_MENU_N;
     std::vector<CUtensorMap> host(n);
     memset(host.data(), 0, n * sizeof(CUtensorMap));
     const cuuint64_t gdim[3] = { (cuuint64_t)2 * c->vx, (cuuint64_t)c->vy, (cuuint64_t)c->vz };
     const cuuint64_t gstr[2] = { (cuuint64_t)8 * c->vx, (cuuint64_t)8 * c->vx * c->vy };
     const cuuint32_t estr[3] = { 1, 1, 1 };
-    for (int ix = 0; ix < WW_NQX; ++ix)
-        for (int iy = 0; iy < WW_NQ; ++iy)
-            for (int iz = 0; iz < WW_NQ; ++iz) {
-                const int bx = ww_qx_val(ix), by = ww_q_val(iy), bz = ww_q_val(iz);
+    for (int ix = 0; ix < WW_MENU_NX; ++ix)
+        for (int by = 1; by <= WW_MENU_N; ++by)
+            for (int bz = 1; bz <= WW_MENU_N; ++bz) {
+                const int bx = WW_MENU_X0 + 2 * ix;
                 if (bx * by * bz > WW_WIN_VOX) continue;
                 const cuuint32_t box[3] = { (cuuint32_t)2 * bx, (cuuint32_t)by, (cuuint32_t)bz };
-                const CUresult r = enc(&host[(ix * WW_NQ + iy) * WW_NQ + iz], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstr, box, estr,
+                const CUresult r = enc(&host[ww_menu_index(bx, by, bz)], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstr, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) {
@@ -593,7 +662,7 @@ static int ww_grid(const svr_context* c, uint32_t n_tiles)
     return (int)(need < want ? need : want);
 }
 
-int svr_launch_window_scatter(svr_context* c, int mode)
+int svr_launch_window_scatter(svr_context* c, int mode, int only_class)
 {
     if (c->n_tiles == 0) return 0;
     WWScatterArgs a{};
@@ -602,8 +671,10 @@ int svr_launch_window_scatter(svr_context* c, int mode)
     a.slices = c->slices; a.weights = c->weights; a.simslices = c->simslices; a.slice_weights = c->slice_weights; a.scales = c->scales;
     a.psf_sums = c->psf_sums; a.geom = c->geom; a.acc2 = c->acc2; a.mask = c->mask_u8; a.voxel_flag = c->voxel_flag;
     a.slice_count = c->slice_count; a.maps = (const CUtensorMap*)c->maps_acc;
-    a.flush_tma = (c->tune_scatter == 2 && c->maps_acc) ? 1 : 0;
-    SVR_CUDA(c, cudaMemsetAsync(c->ww_counter, 0, sizeof(unsigned int), c->stream));
+    a.flush_tma = (c->tune_scatter != 1 && c->maps_acc) ? 1 : 0;
+    a.only_class = only_class;
+    a.stats = c->ww_counter + 8;
+    SVR_CUDA(c, cudaMemsetAsync(c->ww_counter, 0, 40 * sizeof(unsigned int), c->stream));
     const int grid = ww_grid(c, c->n_tiles);
     if (c->flavor == 0) {
         if (mode == 0) {

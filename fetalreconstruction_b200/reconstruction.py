@@ -305,6 +305,7 @@ class Reconstruction:
     def debugVoxelCount(self): return self._debug(8, self.NP, np.int32)
     def debugSlicesRestored(self): return self._debug(9, self.NP, np.float32)
     def debugScalesDevice(self): return self._debug(10, self.S, np.float32)
+    def debugWindowStats(self): return self._debug(12, 32, np.uint32)
 
     # -- multi-rank split phases (include/svr_abi.h, section "multi-rank") ----------------------
     def gaussian_reconstruction_local(self):

@@ -51,8 +51,9 @@ int64_t svr_launch_count(const svr_context *ctx);
 /* Kernel-variant selection for A/B measurements (tools/, bench.py --tune); results agree within float summation order.
  * No reference counterpart (the reference has compile-time switches only, .cuh:53-75). */
 enum {
-    SVR_TUNE_SCATTER = 0,   /* K1 pass 2 / K3: 0 = paired per-lane reductions, 1 = warp windows + SIMT flush,
-                               2 = warp windows + TMA reduce flush (default) */
+    SVR_TUNE_SCATTER = 0,   /* K1 pass 2 / K3: 0 = paired per-lane reductions (default: fastest on every orientation measured,
+                               profiles/r02_ww_ab.txt), 1 = warp windows + SIMT flush, 2 = warp windows + TMA reduce flush,
+                               3 = paired for slices aligned with the volume axes and warp windows for the others */
     SVR_TUNE_SIMULATE = 1   /* K2: 0 = per-tap loads + staged rows (default), 1 = TMA-staged windows for every tile,
                                2 = windows for through-plane slices only */
 };
@@ -183,7 +184,8 @@ enum svr_debug_kind {
     SVR_DBG_VOXEL_COUNT = 8,    /* int  [S*Ny*Nx] */
     SVR_DBG_SLICES_RESTORED = 9,/* float[S*Ny*Nx] */
     SVR_DBG_SCALES_DEVICE = 10, /* float[S]: the scale vector the kernels see */
-    SVR_DBG_MASK = 11           /* float[V] */
+    SVR_DBG_MASK = 11,          /* float[V] */
+    SVR_DBG_WW_STATS = 12       /* unsigned[32]: window-plan statistics of the last scatter launch (svr_window.cu: ww_count) */
 };
 int svr_debug_get(svr_context *ctx, int kind, void *out);
 

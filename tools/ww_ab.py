@@ -43,10 +43,14 @@ for st in stacks:
     out = {"stack": st, "slice_x_axis": [round(float(v), 3) for v in a.xaxis], "slice_y_axis": [round(float(v), 3) for v in a.yaxis],
            "pixels": int(np.count_nonzero(b.debugv_PSF_sums()))}
     ref_acc = ref_vol = ref_sim = None
-    for v in (0, 1, 2):
+    for v in (0, 1, 2, 3):
         b.set_tuning(b.TUNE_SCATTER, v)
         out[f"K3_scatter{v}_ms"] = round(timed(b, "superres", lambda: b.superresolution_local(sw)), 3)
         addon, cmap = b.debugAddon(), b.debugConfidenceMap()
+        if v in (1, 2):
+            st_ = b.debugWindowStats()
+            out[f"K3_scatter{v}_plan"] = {"S1_2_4_8_16": st_[0:5].tolist(), "no_window": int(st_[5]), "degree1to8": st_[8:16].tolist(),
+                                          "tma": int(st_[16]), "general": int(st_[17]), "shared_centre_tiles": int(st_[18]), "fallback_px": int(st_[19])}
         if v == 0:
             ref_acc = (addon, cmap)
         else:
@@ -61,7 +65,7 @@ for st in stacks:
             out[f"K2_sim{v}_vs0"] = {"sim": rel(sims[v][0], sims[0][0]), "simw": rel(sims[v][1], sims[0][1]),
                                      "inside_diff": int(np.count_nonzero(sims[v][2] != sims[0][2]))}
     b.set_tuning(b.TUNE_SIMULATE, 0)
-    for v in (0, 1, 2):
+    for v in (0, 1, 2, 3):
         b.set_tuning(b.TUNE_SCATTER, v)
         out[f"K1_scatter{v}_ms"] = round(timed(b, "gaussian", lambda: b.gaussian_reconstruction_local()), 3)
         vn = b.gaussian_reconstruction_finish()
