@@ -100,6 +100,7 @@ int pvr_create(svr_context** out, int device)
 int pvr_recon_init(svr_context* c, int sx, int sy, int sz, float dx, float dy, float dz, const float recon_w2i[16],
                    const float recon_i2w[16])
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && recon_w2i && recon_i2w, "pvr_recon_init: NULL argument");
     if (int r = svr_init_reconstruction_volume(c, sx, sy, sz, dx, dy, dz, nullptr)) return r;
     memcpy(c->recon_i2w, recon_i2w, 16 * sizeof(float));
@@ -110,6 +111,7 @@ int pvr_recon_init(svr_context* c, int sx, int sy, int sz, float dx, float dy, f
 
 int pvr_recon_set_mask(svr_context* c, const signed char* mask)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && mask && c->V > 0, "pvr_recon_set_mask: volume not initialised or NULL mask");
     std::vector<float> f(c->V);
     for (size_t i = 0; i < c->V; ++i) f[i] = (float)mask[i];
@@ -118,6 +120,7 @@ int pvr_recon_set_mask(svr_context* c, const signed char* mask)
 
 int pvr_recon_reset(svr_context* c)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && c->recon, "pvr_recon_reset: volume not initialised");
     SVR_CUDA(c, cudaMemsetAsync(c->recon, 0, c->V * sizeof(float), c->stream));
     SVR_CUDA(c, cudaMemsetAsync(c->volw, 0, c->V * sizeof(float), c->stream));
@@ -127,6 +130,7 @@ int pvr_recon_reset(svr_context* c)
 
 int pvr_recon_reset_addon_cmap(svr_context* c)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && c->recon, "pvr_recon_reset_addon_cmap: volume not initialised");
     SVR_CUDA(c, cudaMemsetAsync(c->acc2, 0, c->V * sizeof(float2), c->stream));
     return sync_(c);
@@ -134,6 +138,7 @@ int pvr_recon_reset_addon_cmap(svr_context* c)
 
 int pvr_recon_equalize(svr_context* c)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && c->recon, "pvr_recon_equalize: volume not initialised");
     if (svr_launch_equalize_inplace(c)) return 1;
     return sync_(c);
@@ -144,6 +149,7 @@ int pvr_recon_copy_to_host(svr_context* c, float* data) { return svr_sync_cpu(c,
 
 int pvr_patches_init(svr_context* c, int pbx, int pby, int n_stacks, const int* patches_per_stack, const float* stack_dims)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && c->flavor == 1, "pvr_patches_init: not a PVR context");
     PVR_REQUIRE(c, pbx > 0 && pby > 0 && n_stacks >= 0 && (n_stacks == 0 || (patches_per_stack && stack_dims)),
                 "pvr_patches_init: bad argument");
@@ -179,12 +185,14 @@ int pvr_patches_init(svr_context* c, int pbx, int pby, int n_stacks, const int* 
 int pvr_patches_set_matrices(svr_context* c, const float* i2w, const float* w2i, const float* transformation,
                              const float* inv_transformation)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && c->pvr, "pvr_patches_set_matrices: call pvr_patches_init first");
     return svr_set_slice_matrices(c, transformation, inv_transformation, i2w, w2i, c->recon_i2w, c->recon_w2i);
 }
 
 int pvr_patches_set_spx_masks(svr_context* c, const char* masks, int use_spx)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && c->pvr, "pvr_patches_set_spx_masks: call pvr_patches_init first");
     if (masks && c->S) {
         SVR_CUDA(c, cudaMemcpyAsync(c->spx, masks, (size_t)c->S * 4096, cudaMemcpyHostToDevice, c->stream));
@@ -196,6 +204,7 @@ int pvr_patches_set_spx_masks(svr_context* c, const char* masks, int use_spx)
 
 int pvr_patches_copy_from_host(svr_context* c, const float* cube)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && c->pvr, "pvr_patches_copy_from_host: call pvr_patches_init first");
     return svr_fill_slices(c, cube, nullptr, nullptr);
 }
@@ -204,11 +213,13 @@ int pvr_patches_copy_to_host(svr_context* c, float* cube) { return svr_debug_get
 
 int pvr_set_psf(svr_context* c, const int psf_size[3], const float psf_i2w[16], float quality_factor)
 {
+    SVR_ENTRY(c);
     return svr_generate_psf_volume(c, psf_size, psf_i2w, quality_factor);
 }
 
 int pvr_init_patch_based_recon(svr_context* c, int stack, const float* stack_data, int sx, int sy, int sz, const float stack_w2i[16])
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_init_patch_based_recon")) return r;
     PvrState* p = (PvrState*)c->pvr;
     PVR_REQUIRE(c, stack >= 0 && stack < p->n_stacks && stack_data && stack_w2i && sx > 0 && sy > 0 && sz > 0,
@@ -236,6 +247,7 @@ int pvr_init_patch_based_recon(svr_context* c, int stack, const float* stack_dat
 
 int pvr_psf_reconstruction(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_psf_reconstruction")) return r;
     if (svr_launch_gaussian_scatter(c)) return 1;
     if (svr_launch_unpack_acc(c)) return 1;
@@ -246,6 +258,7 @@ int pvr_psf_reconstruction(svr_context* c)
 // accumulator, let the host all-reduce svr_device_buffer(SVR_BUF_ACCUMULATOR) over the ranks, then unpack it.
 int pvr_psf_reconstruction_local(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_psf_reconstruction_local")) return r;
     if (svr_launch_gaussian_scatter(c)) return 1;
     return sync_(c);
@@ -253,6 +266,7 @@ int pvr_psf_reconstruction_local(svr_context* c)
 
 int pvr_psf_reconstruction_finish(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_psf_reconstruction_finish")) return r;
     if (svr_launch_unpack_acc(c)) return 1;
     return sync_(c);
@@ -260,6 +274,7 @@ int pvr_psf_reconstruction_finish(svr_context* c)
 
 int pvr_simulate_patches(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_simulate_patches")) return r;
     if (svr_launch_pack_volume(c)) return 1;
     if (svr_launch_simulate(c)) return 1;
@@ -268,6 +283,7 @@ int pvr_simulate_patches(svr_context* c)
 
 int pvr_superresolution_run(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_superresolution_run")) return r;
     if (svr_launch_superres_scatter(c)) return 1;
     return sync_(c);
@@ -275,6 +291,7 @@ int pvr_superresolution_run(svr_context* c)
 
 int pvr_superresolution_regularize(svr_context* c, int adaptive, float alpha, float min_i, float max_i, float delta, float lambda)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_superresolution_regularize")) return r;
     if (svr_launch_regularize(c, adaptive, alpha, min_i, max_i, delta, lambda)) return 1;
     return sync_(c);
@@ -282,6 +299,7 @@ int pvr_superresolution_regularize(svr_context* c, int adaptive, float alpha, fl
 
 int pvr_rs_initialize_em_values(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_rs_initialize_em_values")) return r;
     std::vector<float> ones((size_t)std::max(c->S, 1), 1.0f);       // resetScaleAndWeights
     if (int r = svr_update_scale_vector(c, ones.data(), ones.data())) return r;
@@ -290,18 +308,21 @@ int pvr_rs_initialize_em_values(svr_context* c)
 
 int pvr_rs_initialize_robust_statistics(svr_context* c, float* sigma)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_rs_initialize_robust_statistics")) return r;
     return svr_initialize_robust_statistics(c, sigma);
 }
 
 int pvr_rs_estep_device(svr_context* c, float m, float sigma, float mix, float* patch_potential)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_rs_estep_device")) return r;
     return svr_estep(c, m, sigma, mix, patch_potential);
 }
 
 int pvr_rs_get_scales_weights(svr_context* c, float* scales, float* patch_weights)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && c->pvr && scales && patch_weights, "pvr_rs_get_scales_weights: bad argument");
     for (int i = 0; i < c->S; ++i) { scales[i] = c->h_scales[i]; patch_weights[i] = c->h_slice_weights[i]; }
     return 0;
@@ -309,6 +330,7 @@ int pvr_rs_get_scales_weights(svr_context* c, float* scales, float* patch_weight
 
 int pvr_rs_set_scales_weights(svr_context* c, const float* scales, const float* patch_weights)
 {
+    SVR_ENTRY(c);
     PVR_REQUIRE(c, c && c->pvr, "pvr_rs_set_scales_weights: call pvr_patches_init first");
     return svr_update_scale_vector(c, scales, patch_weights);
 }
@@ -386,12 +408,14 @@ int pvr_host_patch_em(int n_stacks, const int* patches_per_stack, const float* p
 
 int pvr_rs_mstep(svr_context* c, int iter, float step, float* sigma, float* mix, float* m)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_rs_mstep")) return r;
     return svr_mstep(c, iter, step, sigma, mix, m);       // same host arithmetic (FLT_MAX / FLT_MIN seeds, 6.28f floor)
 }
 
 int pvr_rs_scale(svr_context* c, float* scale_vec)
 {
+    SVR_ENTRY(c);
     if (int r = pvr_ready(c, "pvr_rs_scale")) return r;
     PVR_REQUIRE(c, scale_vec, "pvr_rs_scale: NULL output");
     if (c->S == 0) return 0;

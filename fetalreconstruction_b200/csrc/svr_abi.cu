@@ -100,6 +100,7 @@ int svr_create(svr_context** out, int device)
 
 int svr_destroy(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
@@ -124,6 +125,7 @@ int svr_destroy(svr_context* c)
 
 int svr_set_stream(svr_context* c, void* cuda_stream)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     SVR_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
@@ -132,6 +134,7 @@ int svr_set_stream(svr_context* c, void* cuda_stream)
 
 int svr_synchronize(svr_context* c)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     SVR_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -141,6 +144,7 @@ int64_t svr_launch_count(const svr_context* c) { return c ? c->launches : 0; }
 
 int svr_set_tuning(svr_context* c, int key, int value)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     switch (key) {
     case SVR_TUNE_SCATTER: REQUIRE(c, value >= 0 && value <= 3, "svr_set_tuning: SVR_TUNE_SCATTER takes 0 .. 3"); c->tune_scatter = value; return 0;
@@ -151,6 +155,7 @@ int svr_set_tuning(svr_context* c, int key, int value)
 
 int svr_profile_enable(svr_context* c, int on)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     if (!on) prof_fold(c);
     c->prof_on = on != 0;
@@ -158,6 +163,7 @@ int svr_profile_enable(svr_context* c, int on)
 }
 int svr_profile_read(svr_context* c, int kind, double* total_ms, int64_t* launches)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && kind >= 0 && kind < SVR_K_COUNT, "svr_profile_read: bad argument");
     prof_fold(c);
     if (total_ms) *total_ms = c->prof_ms[kind];
@@ -166,6 +172,7 @@ int svr_profile_read(svr_context* c, int kind, double* total_ms, int64_t* launch
 }
 int svr_profile_reset(svr_context* c)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     prof_fold(c);
     for (int i = 0; i < 8; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
@@ -188,6 +195,7 @@ static int download(svr_context* c, void* dst, const void* src, size_t bytes)
 
 int svr_init_reconstruction_volume(svr_context* c, int sx, int sy, int sz, float dx, float dy, float dz, const float* data)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     REQUIRE(c, sx > 0 && sy > 0 && sz > 0, "svr_init_reconstruction_volume: bad size");
     REQUIRE(c, (double)sx * sy * sz < 2147483647.0, "svr_init_reconstruction_volume: volume too large for 32-bit voxel indices");
@@ -218,6 +226,7 @@ __global__ void mask_to_u8_kernel(size_t V, const float* __restrict__ m, unsigne
 
 int svr_set_mask(svr_context* c, int sx, int sy, int sz, const float* mask)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     REQUIRE(c, c->V > 0, "svr_set_mask: call svr_init_reconstruction_volume first");
     REQUIRE(c, sx == c->vx && sy == c->vy && sz == c->vz, "svr_set_mask: mask grid differs from the volume grid");
@@ -231,9 +240,12 @@ int svr_set_mask(svr_context* c, int sx, int sy, int sz, const float* mask)
 
 int svr_init_storage_volumes(svr_context* c, int Nx, int Ny, int S)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     REQUIRE(c, Nx > 0 && Ny > 0 && S >= 0, "svr_init_storage_volumes: bad size");
     REQUIRE(c, (double)Nx * Ny * (double)std::max(S, 1) < 2147483647.0, "svr_init_storage_volumes: slice cube too large for 32-bit pixel indices");
+    // the registration and PVR patch kernels put the slice / patch index on gridDim.y / gridDim.z (limit 65535)
+    REQUIRE(c, S <= 65535, "svr_init_storage_volumes: more than 65535 slices / patches per context (shard them over more ranks)");
     SVR_CUDA(c, cudaSetDevice(c->device));
     c->Nx = Nx; c->Ny = Ny; c->S = S; c->NP = (size_t)Nx * Ny * S;
     const size_t NP = c->NP, Sn = (size_t)std::max(S, 1);
@@ -269,6 +281,7 @@ int svr_init_storage_volumes(svr_context* c, int Nx, int Ny, int S)
 
 int svr_fill_slices(svr_context* c, const float* cube, const int* sizesX, const int* sizesY)
 {
+    SVR_ENTRY(c);
     (void)sizesX; (void)sizesY;
     REQUIRE(c, c, "null context");
     REQUIRE(c, c->slices || c->NP == 0, "svr_fill_slices: call svr_init_storage_volumes first");
@@ -283,6 +296,7 @@ int svr_fill_slices(svr_context* c, const float* cube, const int* sizesX, const 
 
 int svr_set_slice_dims(svr_context* c, const float* dims_xyz, float quality_factor)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     REQUIRE(c, c->dims || c->S == 0, "svr_set_slice_dims: call svr_init_storage_volumes first");
     c->quality_factor = quality_factor;     // only stored: the PSF support is fixed at 16 (USE_INFINITE_PSF_SUPPORT)
@@ -297,6 +311,7 @@ int svr_set_slice_dims(svr_context* c, const float* dims_xyz, float quality_fact
 int svr_set_slice_matrices(svr_context* c, const float* T, const float* Tinv, const float* I2W, const float* W2I,
                            const float recon_i2w[16], const float recon_w2i[16])
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     REQUIRE(c, c->mats || c->S == 0, "svr_set_slice_matrices: call svr_init_storage_volumes first");
     REQUIRE(c, recon_i2w && recon_w2i, "svr_set_slice_matrices: volume matrices are NULL");
@@ -318,6 +333,7 @@ int svr_set_slice_matrices(svr_context* c, const float* T, const float* Tinv, co
 
 int svr_generate_psf_volume(svr_context* c, const int psf_size[3], const float psf_i2w[16], float quality_factor)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     REQUIRE(c, psf_size && psf_i2w, "svr_generate_psf_volume: NULL argument");
     c->quality_factor = quality_factor;
@@ -330,6 +346,7 @@ int svr_generate_psf_volume(svr_context* c, const int psf_size[3], const float p
 
 int svr_update_scale_vector(svr_context* c, const float* scales, const float* slice_weights)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     REQUIRE(c, c->scales || c->S == 0, "svr_update_scale_vector: call svr_init_storage_volumes first");
     if (c->S == 0) return 0;
@@ -345,6 +362,7 @@ int svr_update_scale_vector(svr_context* c, const float* scales, const float* sl
 
 int svr_update_slice_weights(svr_context* c, const float* slice_weights)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     if (c->S == 0) return 0;
     REQUIRE(c, slice_weights, "svr_update_slice_weights: NULL argument");
@@ -354,6 +372,7 @@ int svr_update_slice_weights(svr_context* c, const float* slice_weights)
 
 int svr_update_reconstructed(svr_context* c, const float* data)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && c->recon && data, "svr_update_reconstructed: volume not initialised or NULL data");
     return upload(c, c->recon, data, c->V * sizeof(float));
 }
@@ -369,6 +388,7 @@ static int ready(svr_context* c, const char* who)
 
 int svr_initialize_em_values(svr_context* c)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     if (c->NP == 0) return 0;
     if (svr_launch_init_em(c)) return 1;
@@ -378,6 +398,7 @@ int svr_initialize_em_values(svr_context* c)
 
 int svr_gaussian_reconstruction_local(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (int r = ready(c, "svr_gaussian_reconstruction")) return r;
     const size_t NP = c->NP;
     if (NP) {
@@ -399,6 +420,7 @@ int svr_gaussian_reconstruction_local(svr_context* c)
 
 int svr_gaussian_reconstruction_finish(svr_context* c, int* voxel_num)
 {
+    SVR_ENTRY(c);
     if (int r = ready(c, "svr_gaussian_reconstruction")) return r;
     if (svr_launch_equalize(c)) return 1;
     if (voxel_num && c->S) return download(c, voxel_num, c->slice_count, c->S * sizeof(int));
@@ -408,12 +430,14 @@ int svr_gaussian_reconstruction_finish(svr_context* c, int* voxel_num)
 
 int svr_gaussian_reconstruction(svr_context* c, int* voxel_num)
 {
+    SVR_ENTRY(c);
     if (int r = svr_gaussian_reconstruction_local(c)) return r;
     return svr_gaussian_reconstruction_finish(c, voxel_num);
 }
 
 int svr_simulate_slices(svr_context* c, unsigned char* slice_inside)
 {
+    SVR_ENTRY(c);
     if (int r = ready(c, "svr_simulate_slices")) return r;
     if (svr_launch_pack_volume(c)) return 1;
     if (svr_launch_simulate(c)) return 1;
@@ -429,6 +453,7 @@ int svr_simulate_slices(svr_context* c, unsigned char* slice_inside)
 
 int svr_initialize_robust_statistics_local(svr_context* c, double sums2[2])
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && sums2, "svr_initialize_robust_statistics: NULL argument");
     sums2[0] = sums2[1] = 0;
     if (c->NP == 0) return 0;
@@ -437,6 +462,7 @@ int svr_initialize_robust_statistics_local(svr_context* c, double sums2[2])
 
 int svr_initialize_robust_statistics(svr_context* c, float* sigma)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && sigma, "svr_initialize_robust_statistics: NULL argument");
     double s2[2];
     if (int r = svr_initialize_robust_statistics_local(c, s2)) return r;
@@ -446,6 +472,7 @@ int svr_initialize_robust_statistics(svr_context* c, float* sigma)
 
 int svr_estep(svr_context* c, float m, float sigma, float mix, float* slice_potential)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     if (c->NP == 0) return 0;
     if (svr_launch_estep(c, m, sigma, mix)) return 1;
@@ -456,6 +483,7 @@ int svr_estep(svr_context* c, float m, float sigma, float mix, float* slice_pote
 
 int svr_mstep_local(svr_context* c, double sums5[5])
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && sums5, "svr_mstep: NULL argument");
     for (int i = 0; i < 5; ++i) sums5[i] = 0;
     if (c->NP == 0) return 0;
@@ -479,6 +507,7 @@ int svr_mstep_finish(const double sums5[5], int iter, float step, float* sigma_,
 
 int svr_mstep(svr_context* c, int iter, float step, float* sigma, float* mix, float* m)
 {
+    SVR_ENTRY(c);
     double s5[5];
     if (int r = svr_mstep_local(c, s5)) return r;
     return svr_mstep_finish(s5, iter, step, sigma, mix, m);
@@ -486,6 +515,7 @@ int svr_mstep(svr_context* c, int iter, float step, float* sigma, float* mix, fl
 
 int svr_calculate_scale_vector(svr_context* c, float* scale_vec)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && scale_vec, "svr_calculate_scale_vector: NULL argument");
     if (c->S == 0) return 0;
     if (svr_launch_scale(c)) return 1;
@@ -502,6 +532,7 @@ int svr_calculate_scale_vector(svr_context* c, float* scale_vec)
 
 int svr_superresolution_local(svr_context* c, const float* slice_weight)
 {
+    SVR_ENTRY(c);
     if (int r = ready(c, "svr_superresolution")) return r;
     if (slice_weight && c->S) if (int r = svr_update_slice_weights(c, slice_weight)) return r;
     SVR_CUDA(c, cudaMemsetAsync(c->acc2, 0, c->V * sizeof(float2), c->stream));
@@ -512,6 +543,7 @@ int svr_superresolution_local(svr_context* c, const float* slice_weight)
 
 int svr_superresolution_finish(svr_context* c, int adaptive, float alpha, float min_i, float max_i, float delta, float lambda)
 {
+    SVR_ENTRY(c);
     if (int r = ready(c, "svr_superresolution")) return r;
     if (svr_launch_regularize(c, adaptive, alpha, min_i, max_i, delta, lambda)) return 1;
     SVR_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -521,6 +553,7 @@ int svr_superresolution_finish(svr_context* c, int adaptive, float alpha, float 
 int svr_superresolution(svr_context* c, int iter, const float* slice_weight, int adaptive, float alpha, float min_i,
                         float max_i, float delta, float lambda)
 {
+    SVR_ENTRY(c);
     (void)iter;
     if (int r = svr_superresolution_local(c, slice_weight)) return r;
     return svr_superresolution_finish(c, adaptive, alpha, min_i, max_i, delta, lambda);
@@ -528,6 +561,7 @@ int svr_superresolution(svr_context* c, int iter, const float* slice_weight, int
 
 int svr_mask_volume(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (int r = ready(c, "svr_mask_volume")) return r;
     if (svr_launch_mask_volume(c)) return 1;
     SVR_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -536,6 +570,7 @@ int svr_mask_volume(svr_context* c)
 
 int svr_scale_volume_local(svr_context* c, double sums2[2])
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && sums2, "svr_scale_volume: NULL argument");
     sums2[0] = sums2[1] = 0;
     if (c->NP == 0) return 0;
@@ -544,6 +579,7 @@ int svr_scale_volume_local(svr_context* c, double sums2[2])
 
 int svr_scale_volume_apply(svr_context* c, float scale)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && c->recon, "svr_scale_volume: volume not initialised");
     if (svr_launch_scale_volume_apply(c, scale)) return 1;
     SVR_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -552,6 +588,7 @@ int svr_scale_volume_apply(svr_context* c, float scale)
 
 int svr_scale_volume(svr_context* c, float* scale_out)
 {
+    SVR_ENTRY(c);
     double s2[2];
     if (int r = svr_scale_volume_local(c, s2)) return r;
     const float scale = (float)(s2[0] / s2[1]);          // cuda2.cu:3459
@@ -561,6 +598,7 @@ int svr_scale_volume(svr_context* c, float* scale_out)
 
 int svr_restore_slice_intensities(svr_context* c, const float* stack_factors, int n_stacks, const int* stack_index)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && stack_factors && stack_index && n_stacks > 0, "svr_restore_slice_intensities: bad argument");
     if (c->NP == 0) return 0;
     float* d_f = nullptr; int* d_i = nullptr;
@@ -575,18 +613,21 @@ int svr_restore_slice_intensities(svr_context* c, const float* stack_factors, in
 
 int svr_sync_cpu(svr_context* c, float* reconstructed)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && c->recon && reconstructed, "svr_sync_cpu: volume not initialised or NULL output");
     return download(c, reconstructed, c->recon, c->V * sizeof(float));
 }
 
 int svr_get_vol_weights(svr_context* c, float* weights)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && c->volw && weights, "svr_get_vol_weights: volume not initialised or NULL output");
     return download(c, weights, c->volw, c->V * sizeof(float));
 }
 
 int svr_debug_get(svr_context* c, int kind, void* out)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && out, "svr_debug_get: NULL argument");
     switch (kind) {
     case SVR_DBG_WEIGHTS: return download(c, out, c->weights, c->NP * sizeof(float));
@@ -619,6 +660,7 @@ int svr_debug_get(svr_context* c, int kind, void* out)
 
 int svr_device_buffer(svr_context* c, int kind, void** dev_ptr, size_t* nbytes)
 {
+    SVR_ENTRY(c);
     REQUIRE(c, c && dev_ptr && nbytes, "svr_device_buffer: NULL argument");
     switch (kind) {
     case SVR_BUF_ACCUMULATOR: *dev_ptr = c->acc2; *nbytes = c->V * sizeof(float2); return 0;

@@ -109,6 +109,23 @@ int svr_fail(svr_context* ctx, const char* what, cudaError_t e, const char* file
         if (_e != cudaSuccess) return svr_fail((ctx), "kernel launch", _e, __FILE__, __LINE__); \
     } while (0)
 
+// Every extern "C" entry point that takes a context runs on the context's device whatever device is current in the calling
+// thread, and restores the caller's device on return (a host that drives several contexts from one thread, as the
+// reference's own host loop over devicesToUse does).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const svr_context* c)
+    {
+        if (!c) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != c->device) { prev = cur; cudaSetDevice(c->device); }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define SVR_ENTRY(ctx) DeviceGuard _svr_device_guard(ctx)
+
 // RAII event bracket around a launch (no-op unless svr_profile_enable(ctx, 1))
 struct ProfScope {
     svr_context* c; int idx;

@@ -510,6 +510,7 @@ extern "C" {
 
 int svr_reg_init_storage(svr_context* c, int W, int H, int S, float dx, float dy, float dz)
 {
+    SVR_ENTRY(c);
     if (!c) return 2;
     (void)dy; (void)dz;
     REG_REQUIRE(c, W > 0 && H > 0 && S >= 0, "svr_reg_init_storage: bad size");
@@ -536,6 +537,7 @@ int svr_reg_init_storage(svr_context* c, int W, int H, int S, float dx, float dy
 
 int svr_reg_fill_slices(svr_context* c, const float* cube, const float* slices_resampled_i2w)
 {
+    SVR_ENTRY(c);
     if (!c) return 2;
     RegState* r = (RegState*)c->reg;
     REG_REQUIRE(c, r, "svr_reg_fill_slices: call svr_reg_init_storage first");
@@ -598,6 +600,7 @@ reg_resample_kernel(int S, int W, int H, int Nx, int Ny, const float* __restrict
 int svr_reg_resample_slices(svr_context* c, const double* src_from_out, const int* in_sizes, const int* out_sizes,
                             const float* slices_resampled_i2w)
 {
+    SVR_ENTRY(c);
     if (!c) return 2;
     RegState* r = (RegState*)c->reg;
     REG_REQUIRE(c, r, "svr_reg_resample_slices: call svr_reg_init_storage first");
@@ -636,6 +639,7 @@ int svr_reg_resample_slices(svr_context* c, const double* src_from_out, const in
 
 int svr_reg_update_slices_i2w(svr_context* c, const float* ofs)
 {
+    SVR_ENTRY(c);
     if (!c) return 2;
     RegState* r = (RegState*)c->reg;
     REG_REQUIRE(c, r, "svr_reg_update_slices_i2w: call svr_reg_init_storage first");
@@ -650,6 +654,7 @@ int svr_reg_update_slices_i2w(svr_context* c, const float* ofs)
 
 int svr_reg_prepare(svr_context* c)
 {
+    SVR_ENTRY(c);
     if (!c) return 2;
     RegState* r = (RegState*)c->reg;
     REG_REQUIRE(c, r, "svr_reg_prepare: call svr_reg_init_storage first");
@@ -690,6 +695,7 @@ int svr_reg_prepare(svr_context* c)
 
 int svr_reg_set_schedule(svr_context* c, int n_levels, int n_steps, int n_iterations)
 {
+    SVR_ENTRY(c);
     if (!c) return 2;
     RegState* r = (RegState*)c->reg;
     REG_REQUIRE(c, r, "svr_reg_set_schedule: call svr_reg_init_storage first");
@@ -700,6 +706,7 @@ int svr_reg_set_schedule(svr_context* c, int n_levels, int n_steps, int n_iterat
 
 int svr_reg_evaluate(svr_context* c, const float* transforms, int level, float* similarity)
 {
+    SVR_ENTRY(c);
     if (!c) return 2;
     RegState* r = (RegState*)c->reg;
     if (reg_check_ready(c, r, "svr_reg_evaluate")) return 2;
@@ -791,12 +798,14 @@ int svr_reg_register(svr_context* c, float* transforms)
 
 int64_t svr_reg_evaluations(const svr_context* c)
 {
+    SVR_ENTRY(c);
     const RegState* r = c ? (const RegState*)c->reg : nullptr;
     return r ? r->evals : 0;
 }
 
 int svr_reg_debug_get(svr_context* c, int kind, void* out)
 {
+    SVR_ENTRY(c);
     if (!c) return 2;
     RegState* r = (RegState*)c->reg;
     REG_REQUIRE(c, r && out, "svr_reg_debug_get: no registration storage");

@@ -217,7 +217,10 @@ enum svr_buffer_kind {
     SVR_BUF_RECON = 1        /* float[V] */
 };
 /* Device address + byte size of a context-owned buffer (for collectives issued by the caller on the
- * context's stream).  Valid until svr_destroy / re-initialisation of the volume. */
+ * context's stream).  SVR_BUF_ACCUMULATOR is valid until svr_destroy / re-initialisation of the volume.
+ * SVR_BUF_RECON must be re-queried after every svr_superresolution / svr_superresolution_finish call: the regulariser
+ * writes into a second buffer and the two are swapped (double-buffered, deviation D3), so a cached pointer then refers to
+ * the scratch copy. */
 int svr_device_buffer(svr_context *ctx, int kind, void **dev_ptr, size_t *nbytes);
 
 /* ---- per-kernel device timing (CUDA events on the launching stream; for bench.py's roofline) ---- */

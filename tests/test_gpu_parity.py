@@ -30,8 +30,24 @@ pytestmark = pytest.mark.gpu
 # single flipped epsilon-skip decision moves one pixel's PSF mass by up to a few per cent.
 # volume-level (many-pixel sums)
 VOL_RMS, VOL_MAX = 3e-4, 3e-2
-# slice-level
-PIX_RMS, PIX_P999, PIX_MAX = 5e-4, 2e-3, 8e-2
+# slice-level: RMS, plus a COUNT bound on flipped pixels (at most PIX_FRAC of the pixels, and never fewer than 2 allowed, may be
+# further off than PIX_THR) instead of an open maximum; the maximum itself is bounded by what ONE flipped tap can move
+# (one tap of at most 1.0 against PSF sums of ~40-80: < 5e-2 of the RMS).
+PIX_RMS, PIX_THR, PIX_FRAC, PIX_MAX = 3e-4, 1e-3, 3e-4, 5e-2
+
+_STATS = {}
+
+
+def _dump_stats():
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if _STATS and os.path.isdir(out):
+        with open(os.path.join(out, "r02_parity_stats.json"), "w") as f:
+            json.dump(_STATS, f, indent=1)
+
+
+import atexit
+atexit.register(_dump_stats)
 
 
 def _gpu():
@@ -41,18 +57,22 @@ def _gpu():
     return Reconstruction(0)
 
 
-def check_pixels(a, b, name, rms=PIX_RMS, p999=PIX_P999, mx=PIX_MAX):
+def check_pixels(a, b, name, rms=PIX_RMS, thr=PIX_THR, frac=PIX_FRAC, mx=PIX_MAX):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     nz = b[b != 0]
     scale = float(np.sqrt(np.mean(nz ** 2))) if nz.size else 1.0
     d = np.abs(a - b) / scale
-    stats = (float(np.sqrt(np.mean(d ** 2))), float(np.quantile(d, 0.999)), float(d.max()))
-    assert stats[0] <= rms and stats[1] <= p999 and stats[2] <= mx, f"{name}: rms/p99.9/max = {stats}"
+    n_off = int(np.count_nonzero(d > thr))
+    allowed = max(2, int(frac * d.size))
+    stats = {"rms": float(np.sqrt(np.mean(d ** 2))), "beyond_thr": n_off, "thr": thr, "allowed": allowed, "max": float(d.max()), "n": int(d.size)}
+    _STATS[name] = stats
+    assert stats["rms"] <= rms and n_off <= allowed and stats["max"] <= mx, f"{name}: {stats} (bounds: rms {rms}, max {mx})"
     return stats
 
 
 def check_volume(a, b, name, rms=VOL_RMS, mx=VOL_MAX):
     m, r = rel_stats(a, b)
+    _STATS[name] = {"rms": r, "max": m}
     assert r <= rms and m <= mx, f"{name}: rms/max = {(r, m)}"
     return r, m
 
@@ -109,7 +129,8 @@ def test_em_steps_and_superresolution(pair):
     # identical parameters on both sides from here on, so each kernel is compared on its own
     pg, po = g.EStep(m, sig_o, 0.9), o.EStep(m, sig_o, 0.9)
     np.testing.assert_allclose(pg, po, rtol=5e-3, atol=1e-4)
-    check_pixels(g.debugWeights(), o.debugWeights(), "EStep weights", rms=2e-3, p999=2e-2, mx=0.5)
+    # measured on B200: rms 1.1e-6, max 1.2e-4, no pixel beyond 1e-3 (profiles/r01_v9_parity_report.txt)
+    check_pixels(g.debugWeights(), o.debugWeights(), "EStep weights", rms=2e-5, thr=1e-3, frac=1e-4, mx=2e-2)
     sg, so = g.CalculateScaleVector(), o.CalculateScaleVector()
     np.testing.assert_allclose(sg, so, rtol=1e-3)
     np.testing.assert_array_equal(g.debugScalesDevice(), 1.0)       # the device lags one call behind
@@ -192,7 +213,7 @@ def test_slices_overhanging_the_volume_and_identity_alignment():
     assert np.isfinite(res["g"][0]).all() and np.isfinite(res["g"][2]).all()
     check_volume(res["g"][0], res["o"][0], "overhang volume", rms=5e-4, mx=2e-2)
     # exactly aligned grids put many taps ON the skip threshold (mirror-image twins), so allow more flips
-    check_pixels(res["g"][1], res["o"][1], "overhang psf sums", rms=2e-2, p999=0.1, mx=0.2)
+    check_pixels(res["g"][1], res["o"][1], "overhang psf sums", rms=2e-2, thr=5e-2, frac=2e-2, mx=0.2)
 
 
 def test_stale_psf_sums_persist_across_calls(small_ds):
@@ -242,6 +263,8 @@ def test_paired_scatter_paths(size, inplane, voxel, vol, why):
         b.SimulateSlices()
         sw = np.ones(ds.S, np.float32); sw[0] = 0.0; sw[2] = 0.4
         pos = ds.slices[ds.slices > 0]
+        # voxel weights: GaussianReconstruction cleared them (cuda2.cu:2402-2411); without an E-step K3 would scatter zeros
+        b.EStep(1.0 / (2.1 * float(pos.max()) - 1.9 * float(pos.min())), 2.0e4, 0.9)
         b.Superresolution(1, sw, False, 1.0, float(pos.min()), float(pos.max()), 150.0, 0.02 * 150.0 * 150.0)
         res[name] = dict(vn=vn, recon0=recon0, volw=volw, psf=psf, addon=b.debugAddon(), cmap=b.debugConfidenceMap(), recon1=b.syncCPU())
     g, o = res["gpu"], res["orc"]
@@ -249,6 +272,7 @@ def test_paired_scatter_paths(size, inplane, voxel, vol, why):
     check_volume(g["recon0"], o["recon0"], "K1 volume: " + why)
     check_volume(g["volw"], o["volw"], "K1 volume weights: " + why)
     check_pixels(g["psf"], o["psf"], "v_PSF_sums: " + why)
+    assert np.count_nonzero(o["addon"]) > 100, "K3 must scatter something: " + why
     check_volume(g["addon"], o["addon"], "K3 addon: " + why, rms=1e-3, mx=8e-2)
     check_volume(g["cmap"], o["cmap"], "K3 confidence map: " + why)
     check_volume(g["recon1"], o["recon1"], "volume after one SR step: " + why)

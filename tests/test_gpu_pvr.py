@@ -12,7 +12,8 @@ from pvr_case import make_pvr_case, setup_backend
 pytestmark = pytest.mark.gpu
 
 VOL_RMS, VOL_MAX = 3e-4, 3e-2
-PIX_RMS, PIX_P999, PIX_MAX = 5e-4, 2e-3, 8e-2
+# RMS + a count bound on flipped pixels (see test_gpu_parity.py) + what one flipped tap can move
+PIX_RMS, PIX_THR, PIX_FRAC, PIX_MAX = 5e-4, 2e-3, 1e-3, 8e-2
 
 
 def _gpu():
@@ -27,8 +28,9 @@ def check_pixels(a, b, name):
     nz = b[b != 0]
     scale = float(np.sqrt(np.mean(nz ** 2))) if nz.size else 1.0
     d = np.abs(a - b) / scale
-    st = (float(np.sqrt(np.mean(d ** 2))), float(np.quantile(d, 0.999)), float(d.max()))
-    assert st[0] <= PIX_RMS and st[1] <= PIX_P999 and st[2] <= PIX_MAX, f"{name}: rms/p99.9/max = {st}"
+    off = int(np.count_nonzero(d > PIX_THR))
+    st = (float(np.sqrt(np.mean(d ** 2))), off, float(d.max()))
+    assert st[0] <= PIX_RMS and off <= max(2, int(PIX_FRAC * d.size)) and st[2] <= PIX_MAX, f"{name}: rms/beyond {PIX_THR}/max = {st} of {d.size}"
 
 
 def check_volume(a, b, name):

@@ -35,10 +35,21 @@ def _ref(name):
     return dict(np.load(os.path.join(HERE, "golden", f"ref_{name}_small.npz")))
 
 
+# flipped epsilon-skip decisions are bounded by COUNT: at most FLIP_FRAC of a field's elements (never fewer than 2 allowed)
+# may be further than FLIP_THR from the reference; the max bound of FIELD is what one flipped tap can move.
+FLIP_THR, FLIP_FRAC = 3e-3, 1.5e-3       # measured: at most 33 of 64 000 (the K3 accumulator of the kernel-by-kernel case)
+
+
 def _check(got, ref, names, tol):
     for n in names:
-        m, r = rel_stats(np.asarray(got[n], np.float64), np.asarray(ref[n], np.float64))
+        a, b = np.asarray(got[n], np.float64), np.asarray(ref[n], np.float64)
+        m, r = rel_stats(a, b)
         assert r <= tol[0] and m <= tol[1], f"{n}: rms/max = {(r, m)} > {tol}"
+        if tol is FIELD and a.size >= 1000:
+            nz = b[b != 0]
+            sc = float(np.sqrt(np.mean(nz ** 2))) if nz.size else 1.0
+            off = int(np.count_nonzero(np.abs(a - b) / sc > FLIP_THR))
+            assert off <= max(2, int(FLIP_FRAC * a.size)), f"{n}: {off} of {a.size} elements beyond {FLIP_THR}"
 
 
 def _steps(backend):
