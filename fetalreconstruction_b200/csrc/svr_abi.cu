@@ -91,6 +91,7 @@ int svr_create(svr_context** out, int device)
     SVR_CUDA(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     if (const char* e = getenv("SVR_TUNE_SCATTER")) { const int v = atoi(e); if (v >= 0 && v <= 3) c->tune_scatter = v; }
+    if (const char* e = getenv("SVR_TUNE_REGULARIZE")) { const int v = atoi(e); if (v == 0 || v == 1) c->tune_regularize = v; }
     if (const char* e = getenv("SVR_TUNE_SIMULATE")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->tune_simulate = v; }
     c->pinned_bytes = 4096;
     SVR_CUDA(nullptr, cudaMallocHost(&c->pinned, c->pinned_bytes));
@@ -149,6 +150,7 @@ int svr_set_tuning(svr_context* c, int key, int value)
     switch (key) {
     case SVR_TUNE_SCATTER: REQUIRE(c, value >= 0 && value <= 3, "svr_set_tuning: SVR_TUNE_SCATTER takes 0 .. 3"); c->tune_scatter = value; return 0;
     case SVR_TUNE_SIMULATE: REQUIRE(c, value >= 0 && value <= 2, "svr_set_tuning: SVR_TUNE_SIMULATE takes 0, 1 or 2"); c->tune_simulate = value; return 0;
+    case SVR_TUNE_REGULARIZE: REQUIRE(c, value == 0 || value == 1, "svr_set_tuning: SVR_TUNE_REGULARIZE takes 0 or 1"); c->tune_regularize = value; return 0;
     default: return fail_msg(c, "svr_set_tuning: unknown key");
     }
 }
@@ -175,7 +177,7 @@ int svr_profile_reset(svr_context* c)
     SVR_ENTRY(c);
     REQUIRE(c, c, "null context");
     prof_fold(c);
-    for (int i = 0; i < 8; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    for (int i = 0; i < 16; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
     return 0;
 }
 
@@ -251,7 +253,7 @@ int svr_init_storage_volumes(svr_context* c, int Nx, int Ny, int S)
     const size_t NP = c->NP, Sn = (size_t)std::max(S, 1);
     if (dev_alloc(c, &c->slices, NP) || dev_alloc(c, &c->slices_restore, NP) || dev_alloc(c, &c->weights, NP) ||
         dev_alloc(c, &c->simslices, NP) || dev_alloc(c, &c->simweights, NP) || dev_alloc(c, &c->siminside, NP) ||
-        dev_alloc(c, &c->psf_sums, NP) || dev_alloc(c, &c->voxel_flag, NP) || dev_alloc(c, &c->valid_idx, NP) || dev_alloc(c, &c->pair_idx, (size_t)std::max(S, 1) * Ny * ((Nx + 1) / 2)) ||
+        dev_alloc(c, &c->psf_sums, NP) || dev_alloc(c, &c->voxel_flag, NP) || dev_alloc(c, &c->valid_idx, NP + 4) || dev_alloc(c, &c->pair_idx, (size_t)std::max(S, 1) * Ny * ((Nx + 1) / 2)) ||
         dev_alloc(c, &c->slice_count, Sn) || dev_alloc(c, &c->slice_inside, Sn) || dev_alloc(c, &c->scales, Sn) ||
         dev_alloc(c, &c->scales_mstep, Sn) || dev_alloc(c, &c->slice_weights, Sn) || dev_alloc(c, &c->slice_tmp, 4 * Sn) ||
         dev_alloc(c, &c->geom, Sn) || dev_alloc(c, &c->mats, 4 * 16 * Sn) || dev_alloc(c, &c->dims, 3 * Sn))

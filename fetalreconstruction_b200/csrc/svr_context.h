@@ -53,6 +53,7 @@ struct svr_context {
     void* maps_pack = nullptr;
     int tune_scatter = 0;          // 0: paired scatter (round 1), 1: warp windows + SIMT flush, 2: warp windows + TMA reduce flush,
                                    // 3: paired for slices aligned with the volume axes, warp windows (TMA flush) for the others
+    int tune_regularize = 1;       // 0: reg_prep_kernel + reg_kernel (round 1), 1: fused K4 + K5 with a shared-memory halo tile
     int tune_simulate = 0;         // 0: per-tap loads (+ staged rows), 1: TMA-staged windows for every tile, 2: windows for through-plane slices only
     int* slice_count = nullptr;    // [S] per-slice voxel_num (deviation D4)
     int* slice_inside = nullptr;   // [S] OR of siminside since the last Gaussian reconstruction
@@ -79,8 +80,8 @@ struct svr_context {
     bool prof_on = false;
     std::vector<ProfPair> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
-    double prof_ms[8] = {0};
-    long long prof_n[8] = {0};
+    double prof_ms[16] = {0};
+    long long prof_n[16] = {0};
 
     VolGeom vg{};
     float recon_i2w[16]{}, recon_w2i[16]{};

@@ -32,56 +32,113 @@ int svr_launch_init_em(svr_context* c)
 __device__ __forceinline__ float G_(float x, float s, float step) { return step * __expf(-x * x / (2.0f * s)) / (sqrtf(6.28f * s)); }
 __device__ __forceinline__ float M_(float m, float step) { return m * step; }
 
-// ---- K7 + K8 fused: EStepKernel3D_tex + slice potentials (cuda2.cu:2766-2813, 2816-2911) ------
-// grid = (chunks, S).  slice_acc[2k] += sum (1-w)^2, slice_acc[2k+1] += n over pixels with simweight > 0.99.
-__global__ void __launch_bounds__(EM_THREADS)
-estep_kernel(int P, const float* __restrict__ slices, const float* __restrict__ simslices,
-             const float* __restrict__ simweights, const float* __restrict__ scales, float m_, float sigma_, float mix_,
-             float* __restrict__ weights, double* __restrict__ slice_acc, int flavor)
+// ---- iteration over the compacted list of pixels != -1 -----------------------------------------------
+// Every robust-statistics kernel only looks at pixels that are not padding (s != -1), 27 % of the padded slice cube at C3.
+// They therefore walk valid_idx (built once per svr_fill_slices, sorted, slice-major) instead of the cube: a thread takes
+// four consecutive list entries with one 128-bit load and gathers the per-pixel values; neighbouring threads read
+// neighbouring pixels, so every 32-byte sector that is fetched is used.  Padding pixels keep weight 0 (init_em_kernel and
+// the memset of svr_gaussian_reconstruction_local put it there and nothing else writes them).
+#define EM_ITEMS 4
+template <class Body>
+__device__ __forceinline__ void em_for_each(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int P, uint32_t t, Body&& body)
 {
-    const int k = blockIdx.y;
-    const size_t base = (size_t)k * P;
-    const float scale = scales[k];
+    const uint32_t base = t * EM_ITEMS;
+    if (base >= n_valid) return;
+    const uint4 q = *reinterpret_cast<const uint4*>(valid_idx + base);       // the list is allocated with 4 entries of slack
+    const uint32_t ids[EM_ITEMS] = { q.x, q.y, q.z, q.w };
+    const uint32_t cnt = min((uint32_t)EM_ITEMS, n_valid - base);
+    uint32_t k = ids[0] / (uint32_t)P, k_end = (k + 1u) * (uint32_t)P;
+#pragma unroll
+    for (int j = 0; j < EM_ITEMS; ++j) {
+        if ((uint32_t)j < cnt) {
+            if (ids[j] >= k_end) { k = ids[j] / (uint32_t)P; k_end = (k + 1u) * (uint32_t)P; }
+            body(ids[j], (int)k);
+        }
+    }
+}
+
+// Per-slice sums of NV values: a thread keeps the sums of its current slice and sends them to slice_acc when the slice
+// changes; at the end a block whose threads all sit in one slice (all but the ~S blocks that straddle a slice boundary)
+// folds them with one block reduction and NV double atomics.
+template <int NV>
+struct SliceSums {
+    float v[NV];
+    int k;
+    __device__ __forceinline__ SliceSums() : k(-1) { for (int i = 0; i < NV; ++i) v[i] = 0.f; }
+    __device__ __forceinline__ void flush(double* __restrict__ slice_acc)
+    {
+        if (k >= 0)
+            for (int i = 0; i < NV; ++i)
+                if (v[i] != 0.f) atomicAdd(&slice_acc[NV * k + i], (double)v[i]);
+        for (int i = 0; i < NV; ++i) v[i] = 0.f;
+    }
+    __device__ __forceinline__ void enter(int kk, double* __restrict__ slice_acc)
+    {
+        if (kk != k) { flush(slice_acc); k = kk; }
+    }
+    __device__ __forceinline__ void finish(double* __restrict__ slice_acc)
+    {
+        __shared__ int s_k;
+        if (threadIdx.x == 0) s_k = k;
+        __syncthreads();
+        const int k0 = s_k;
+        const bool uniform = __syncthreads_and(k == k0 || k < 0) != 0;
+        if (uniform && k0 >= 0) {
+            typedef cub::BlockReduce<float, EM_THREADS> BR;
+            __shared__ typename BR::TempStorage tmp;
+            for (int i = 0; i < NV; ++i) {
+                const float r = BR(tmp).Sum(v[i]);
+                if (threadIdx.x == 0 && r != 0.f) atomicAdd(&slice_acc[NV * k0 + i], (double)r);
+                __syncthreads();
+            }
+        } else {
+            flush(slice_acc);
+        }
+    }
+};
+
+static inline int valid_grid(const svr_context* c) { return divup_i(c->n_valid, EM_THREADS * EM_ITEMS); }
+
+// ---- K7 + K8 fused: EStepKernel3D_tex + slice potentials (cuda2.cu:2766-2813, 2816-2911) ------
+// slice_acc[2k] += sum (1-w)^2, slice_acc[2k+1] += n over pixels with simweight > 0.99.
+__global__ void __launch_bounds__(EM_THREADS)
+estep_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int P, const float* __restrict__ slices,
+             const float* __restrict__ simslices, const float* __restrict__ simweights, const float* __restrict__ scales,
+             float m_, float sigma_, float mix_, float* __restrict__ weights, double* __restrict__ slice_acc, int flavor)
+{
     const float step = flavor == 0 ? SVR_STEP : 0.00001f;
     const float m = M_(m_, step);
-    float sum = 0.f, num = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-        const float s = slices[base + i];
-        const float sw = simweights[base + i];
+    SliceSums<2> acc;
+    em_for_each(n_valid, valid_idx, P, blockIdx.x * EM_THREADS + threadIdx.x, [&](uint32_t i, int k) {
+        acc.enter(k, slice_acc);
+        const float s = slices[i];
+        const float sw = simweights[i];
         float w;
         if (flavor == 0) {
             w = 0.0f;                                     // cudaMemsetAsync(weights, 0) at cuda2.cu:2881
-            if (!((s == -1.0f) || sw <= 0.0f)) {
-                const float e = s * scale - simslices[base + i];
+            if (!(sw <= 0.0f)) {
+                const float e = s * scales[k] - simslices[i];
                 const float g = G_(e, sigma_, step);
                 w = (g * mix_) / (g * mix_ + m * (1.0f - mix_));
             }
         } else {
             // PVR EStepKernel gates on the PREVIOUS weight and leaves gated pixels untouched
             // (patchBasedRobustStatistics_gpu.cu:121-124)
-            w = weights[base + i];
-            if (!((s == -1.0f) || w <= 0.0f)) {
-                const float e = s * scale - simslices[base + i];
+            w = weights[i];
+            if (!(w <= 0.0f)) {
+                const float e = s * scales[k] - simslices[i];
                 const float g = G_(e, sigma_, step);
                 w = (float)((double)(g * mix_) / ((double)(g * mix_) + (double)m * (1.0 - (double)mix_)));
             }
         }
-        weights[base + i] = w;
+        weights[i] = w;
         if ((double)sw > 0.99) {                          // transformSlicePotential compares against a double literal
             const float d = 1.0f - w;
-            sum += d * d;
-            num += 1.0f;
+            acc.v[0] += d * d;
+            acc.v[1] += 1.0f;
         }
-    }
-    typedef cub::BlockReduce<float, EM_THREADS> BR;
-    __shared__ typename BR::TempStorage tmp;
-    const float bs = BR(tmp).Sum(sum);
-    __syncthreads();
-    const float bn = BR(tmp).Sum(num);
-    if (threadIdx.x == 0 && bn > 0.f) {
-        atomicAdd(&slice_acc[2 * k], (double)bs);
-        atomicAdd(&slice_acc[2 * k + 1], (double)bn);
-    }
+    });
+    acc.finish(slice_acc);
 }
 __global__ void potential_finish_kernel(int S, const double* __restrict__ slice_acc, float* __restrict__ out)
 {
@@ -91,24 +148,16 @@ __global__ void potential_finish_kernel(int S, const double* __restrict__ slice_
     out[k] = (n > 0.f) ? sqrtf(s / n) : -1.0f;            // cuda2.cu:2903-2910
 }
 
-static inline dim3 slice_grid(const svr_context* c)
-{
-    const int P = c->Nx * c->Ny;
-    int chunks = divup_i(P, EM_THREADS * 4);
-    const int want = divup_i(c->sm_count * 4, c->S > 0 ? c->S : 1);
-    if (chunks > want) chunks = want;
-    if (chunks < 1) chunks = 1;
-    return dim3(chunks, c->S);
-}
-
 int svr_launch_estep(svr_context* c, float m, float sigma, float mix)
 {
-    ProfScope prof(c, 4);
+    ProfScope prof(c, 6);
     double* acc = c->partials;                            // [2*S] doubles, zeroed
     SVR_CUDA(c, cudaMemsetAsync(acc, 0, sizeof(double) * 2 * c->S, c->stream));
-    estep_kernel<<<slice_grid(c), EM_THREADS, 0, c->stream>>>(c->Nx * c->Ny, c->slices, c->simslices, c->simweights,
-                                                              c->scales, m, sigma, mix, c->weights, acc, c->flavor);
-    SVR_KERNEL_CHECK(c);
+    if (c->n_valid) {
+        estep_kernel<<<valid_grid(c), EM_THREADS, 0, c->stream>>>(c->n_valid, c->valid_idx, c->Nx * c->Ny, c->slices, c->simslices,
+                                                                  c->simweights, c->scales, m, sigma, mix, c->weights, acc, c->flavor);
+        SVR_KERNEL_CHECK(c);
+    }
     potential_finish_kernel<<<divup_i(c->S, 128), 128, 0, c->stream>>>(c->S, acc, c->slice_tmp);
     SVR_KERNEL_CHECK(c);
     return 0;
@@ -116,29 +165,19 @@ int svr_launch_estep(svr_context* c, float m, float sigma, float mix)
 
 // ---- K10: CalculateScaleVector (cuda2.cu:3142-3239) --------------------------------------------
 __global__ void __launch_bounds__(EM_THREADS)
-scale_kernel(int P, const float* __restrict__ slices, const float* __restrict__ weights,
-             const float* __restrict__ simslices, const float* __restrict__ simweights, double* __restrict__ slice_acc)
+scale_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int P, const float* __restrict__ slices,
+             const float* __restrict__ weights, const float* __restrict__ simslices, const float* __restrict__ simweights,
+             double* __restrict__ slice_acc)
 {
-    const int k = blockIdx.y;
-    const size_t base = (size_t)k * P;
-    float num = 0.f, den = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-        const float s = slices[base + i];
-        const float sw = simweights[base + i];
-        if ((s == -1.0f) || sw <= 0.99f) continue;
-        const float w = weights[base + i], ss = simslices[base + i];
-        num += w * s * ss;
-        den += w * s * s;
-    }
-    typedef cub::BlockReduce<float, EM_THREADS> BR;
-    __shared__ typename BR::TempStorage tmp;
-    const float bn = BR(tmp).Sum(num);
-    __syncthreads();
-    const float bd = BR(tmp).Sum(den);
-    if (threadIdx.x == 0 && (bn != 0.f || bd != 0.f)) {
-        atomicAdd(&slice_acc[2 * k], (double)bn);
-        atomicAdd(&slice_acc[2 * k + 1], (double)bd);
-    }
+    SliceSums<2> acc;
+    em_for_each(n_valid, valid_idx, P, blockIdx.x * EM_THREADS + threadIdx.x, [&](uint32_t i, int k) {
+        acc.enter(k, slice_acc);
+        if (simweights[i] <= 0.99f) return;
+        const float s = slices[i], w = weights[i], ss = simslices[i];
+        acc.v[0] += w * s * ss;
+        acc.v[1] += w * s * s;
+    });
+    acc.finish(slice_acc);
 }
 __global__ void scale_finish_kernel(int S, const double* __restrict__ slice_acc, float* __restrict__ out)
 {
@@ -149,12 +188,14 @@ __global__ void scale_finish_kernel(int S, const double* __restrict__ slice_acc,
 }
 int svr_launch_scale(svr_context* c)
 {
-    ProfScope prof(c, 4);
+    ProfScope prof(c, 8);
     double* acc = c->partials;
     SVR_CUDA(c, cudaMemsetAsync(acc, 0, sizeof(double) * 2 * c->S, c->stream));
-    scale_kernel<<<slice_grid(c), EM_THREADS, 0, c->stream>>>(c->Nx * c->Ny, c->slices, c->weights, c->simslices,
-                                                              c->simweights, acc);
-    SVR_KERNEL_CHECK(c);
+    if (c->n_valid) {
+        scale_kernel<<<valid_grid(c), EM_THREADS, 0, c->stream>>>(c->n_valid, c->valid_idx, c->Nx * c->Ny, c->slices, c->weights,
+                                                                  c->simslices, c->simweights, acc);
+        SVR_KERNEL_CHECK(c);
+    }
     scale_finish_kernel<<<divup_i(c->S, 128), 128, 0, c->stream>>>(c->S, acc, c->slice_tmp);
     SVR_KERNEL_CHECK(c);
     return 0;
@@ -190,23 +231,24 @@ fold_partials_kernel(int nblocks, const double* __restrict__ partials, double* _
 
 // ---- K9: MStep statistics (cuda2.cu:2966-3112): {sum e^2 w, sum w, n, min e, max e}; min/max seeded with 0.
 __global__ void __launch_bounds__(EM_THREADS)
-mstep_kernel(size_t NP, int P, const float* __restrict__ slices, const float* __restrict__ weights,
-             const float* __restrict__ simslices, const float* __restrict__ simweights,
+mstep_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int P, const float* __restrict__ slices,
+             const float* __restrict__ weights, const float* __restrict__ simslices, const float* __restrict__ simweights,
              const float* __restrict__ mstep_scales, double* __restrict__ partials)
 {
     float sigma = 0.f, mix = 0.f, num = 0.f, mn = 0.f, mx = 0.f;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < NP; i += (size_t)gridDim.x * blockDim.x) {
-        const float s = slices[i], sw = simweights[i];
-        if (s != -1.0f && sw > 0.99f) {
-            const float e = s * mstep_scales[i / P] - simslices[i];
-            const float w = weights[i];
-            sigma += e * e * w;
-            mix += w;
-            num += 1.0f;
-            mn = fminf(mn, e);
-            mx = fmaxf(mx, e);
-        }
-    }
+    const uint32_t nthreads = gridDim.x * EM_THREADS;
+    for (uint32_t t = blockIdx.x * EM_THREADS + threadIdx.x; t * EM_ITEMS < n_valid; t += nthreads)
+        em_for_each(n_valid, valid_idx, P, t, [&](uint32_t i, int k) {
+            if (simweights[i] > 0.99f) {
+                const float e = slices[i] * mstep_scales[k] - simslices[i];
+                const float w = weights[i];
+                sigma += e * e * w;
+                mix += w;
+                num += 1.0f;
+                mn = fminf(mn, e);
+                mx = fmaxf(mx, e);
+            }
+        });
     typedef cub::BlockReduce<float, EM_THREADS> BR;
     __shared__ typename BR::TempStorage tmp;
     const float r0 = BR(tmp).Sum(sigma); __syncthreads();
@@ -230,11 +272,11 @@ static int read_back(svr_context* c, const double* dsrc, double* out, int n)
 
 int svr_launch_mstep(svr_context* c, double out5[5])
 {
-    ProfScope prof(c, 4);
+    ProfScope prof(c, 7);
     const int nb = c->sm_count * 4;
     double* part = c->partials;                           // [nb*5] + result [8]
     double* res = c->partials + (size_t)nb * 5;
-    mstep_kernel<<<nb, EM_THREADS, 0, c->stream>>>(c->NP, c->Nx * c->Ny, c->slices, c->weights, c->simslices,
+    mstep_kernel<<<nb, EM_THREADS, 0, c->stream>>>(c->n_valid, c->valid_idx, c->Nx * c->Ny, c->slices, c->weights, c->simslices,
                                                    c->simweights, c->scales_mstep, part);
     SVR_KERNEL_CHECK(c);
     fold_partials_kernel<5><<<1, EM_THREADS, 0, c->stream>>>(nb, part, res, 3);
@@ -244,18 +286,20 @@ int svr_launch_mstep(svr_context* c, double out5[5])
 
 // ---- K11: InitializeRobustStatistics (cuda2.cu:2243-2308): {sum (s - sim)^2, n} -----------------
 __global__ void __launch_bounds__(EM_THREADS)
-robust_init_kernel(size_t NP, const float* __restrict__ slices, const unsigned char* __restrict__ siminside,
-                   const float* __restrict__ simslices, const float* __restrict__ simweights, double* __restrict__ partials)
+robust_init_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int P, const float* __restrict__ slices,
+                   const unsigned char* __restrict__ siminside, const float* __restrict__ simslices,
+                   const float* __restrict__ simweights, double* __restrict__ partials)
 {
     float sa = 0.f, sb = 0.f;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < NP; i += (size_t)gridDim.x * blockDim.x) {
-        const float s = slices[i];
-        if (s != -1.0f && siminside[i] == 1 && (double)simweights[i] > 0.99) {
-            const float d = s - simslices[i];
-            sa += d * d;
-            sb += 1.0f;
-        }
-    }
+    const uint32_t nthreads = gridDim.x * EM_THREADS;
+    for (uint32_t t = blockIdx.x * EM_THREADS + threadIdx.x; t * EM_ITEMS < n_valid; t += nthreads)
+        em_for_each(n_valid, valid_idx, P, t, [&](uint32_t i, int) {
+            if (siminside[i] == 1 && (double)simweights[i] > 0.99) {
+                const float d = slices[i] - simslices[i];
+                sa += d * d;
+                sb += 1.0f;
+            }
+        });
     typedef cub::BlockReduce<float, EM_THREADS> BR;
     __shared__ typename BR::TempStorage tmp;
     const float r0 = BR(tmp).Sum(sa); __syncthreads();
@@ -264,11 +308,12 @@ robust_init_kernel(size_t NP, const float* __restrict__ slices, const unsigned c
 }
 int svr_launch_robust_init(svr_context* c, double out2[2])
 {
-    ProfScope prof(c, 4);
+    ProfScope prof(c, 9);
     const int nb = c->sm_count * 4;
     double* part = c->partials;
     double* res = c->partials + (size_t)nb * 5;
-    robust_init_kernel<<<nb, EM_THREADS, 0, c->stream>>>(c->NP, c->slices, c->siminside, c->simslices, c->simweights, part);
+    robust_init_kernel<<<nb, EM_THREADS, 0, c->stream>>>(c->n_valid, c->valid_idx, c->Nx * c->Ny, c->slices, c->siminside, c->simslices,
+                                                         c->simweights, part);
     SVR_KERNEL_CHECK(c);
     fold_partials_kernel<2><<<1, EM_THREADS, 0, c->stream>>>(nb, part, res, 2);
     SVR_KERNEL_CHECK(c);
@@ -277,19 +322,19 @@ int svr_launch_robust_init(svr_context* c, double out2[2])
 
 // ---- K16: ScaleVolume sums (cuda2.cu:3386-3413, 3451-3454) --------------------------------------
 __global__ void __launch_bounds__(EM_THREADS)
-scale_volume_sums_kernel(size_t NP, int P, const float* __restrict__ slices, const float* __restrict__ weights,
-                         const float* __restrict__ simslices, const float* __restrict__ simweights,
-                         const float* __restrict__ slice_weights, double* __restrict__ partials)
+scale_volume_sums_kernel(uint32_t n_valid, const uint32_t* __restrict__ valid_idx, int P, const float* __restrict__ slices,
+                         const float* __restrict__ weights, const float* __restrict__ simslices,
+                         const float* __restrict__ simweights, const float* __restrict__ slice_weights, double* __restrict__ partials)
 {
     float num = 0.f, den = 0.f;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < NP; i += (size_t)gridDim.x * blockDim.x) {
-        const float s = slices[i];
-        if (s == -1.0f) continue;
-        if ((double)simweights[i] <= 0.99) continue;
-        const float ss = simslices[i], w = weights[i], sw = slice_weights[i / P];
-        num += w * sw * s * ss;
-        den += w * sw * ss * ss;
-    }
+    const uint32_t nthreads = gridDim.x * EM_THREADS;
+    for (uint32_t t = blockIdx.x * EM_THREADS + threadIdx.x; t * EM_ITEMS < n_valid; t += nthreads)
+        em_for_each(n_valid, valid_idx, P, t, [&](uint32_t i, int k) {
+            if ((double)simweights[i] <= 0.99) return;
+            const float s = slices[i], ss = simslices[i], w = weights[i], sw = slice_weights[k];
+            num += w * sw * s * ss;
+            den += w * sw * ss * ss;
+        });
     typedef cub::BlockReduce<float, EM_THREADS> BR;
     __shared__ typename BR::TempStorage tmp;
     const float r0 = BR(tmp).Sum(num); __syncthreads();
@@ -301,7 +346,7 @@ int svr_launch_scale_volume_sums(svr_context* c, double out2[2])
     const int nb = c->sm_count * 4;
     double* part = c->partials;
     double* res = c->partials + (size_t)nb * 5;
-    scale_volume_sums_kernel<<<nb, EM_THREADS, 0, c->stream>>>(c->NP, c->Nx * c->Ny, c->slices, c->weights, c->simslices,
+    scale_volume_sums_kernel<<<nb, EM_THREADS, 0, c->stream>>>(c->n_valid, c->valid_idx, c->Nx * c->Ny, c->slices, c->weights, c->simslices,
                                                                c->simweights, c->slice_weights, part);
     SVR_KERNEL_CHECK(c);
     fold_partials_kernel<2><<<1, EM_THREADS, 0, c->stream>>>(nb, part, res, 2);
@@ -436,14 +481,109 @@ reg_kernel(int vx, int vy, int vz, const float* __restrict__ original, const flo
     out[p] = (valW > 0.0f) ? val / valW : 0.0f;
 }
 
+// Fused K4 + K5 (round 2).  reg_prep_kernel + reg_kernel above read, per voxel, 26 neighbours of three volumes through L1/L2
+// (measured 1.22 ms at 256^3 = 6 % of the HBM rate for its 28 V algorithmic bytes).  Here a CTA stages a tile of
+// 32 x 8 x 8 voxels plus a one-voxel halo in shared memory -- computing the K4 update (mask, normalisation, gradient step,
+// clamp) on the fly for tile AND halo, so the post-step volume is never written to HBM -- and evaluates the 13-direction
+// smoothing from shared memory.  Same arithmetic and operation order per voxel as the two kernels (they remain the
+// fallback and the parity reference: tests/test_gpu_parity.py compares both against the oracle).
+constexpr int RT_X = 32, RT_Y = 8, RT_Z = 8;
+constexpr int RH_X = RT_X + 2, RH_Y = RT_Y + 2, RH_Z = RT_Z + 2;
+
+__global__ void __launch_bounds__(256)
+regularize_fused_kernel(int vx, int vy, int vz, const float* __restrict__ recon, float2* __restrict__ acc2,
+                        const unsigned char* __restrict__ mask, float* __restrict__ out, int adaptive, float alpha, float min_i,
+                        float max_i, float delta, float lambda, int flavor)
+{
+    __shared__ float s_org[RH_Z][RH_Y][RH_X];      // original (untouched) volume
+    __shared__ float s_post[RH_Z][RH_Y][RH_X];     // after the gradient step + clamp (K4)
+    __shared__ float s_cm[RH_Z][RH_Y][RH_X];       // confidence map after K4 (-1 marks voxels outside the volume)
+    const int bx0 = blockIdx.x * RT_X - 1, by0 = blockIdx.y * RT_Y - 1, bz0 = blockIdx.z * RT_Z - 1;
+    for (int i = threadIdx.x; i < RH_X * RH_Y * RH_Z; i += blockDim.x) {
+        const int lx = i % RH_X, ly = (i / RH_X) % RH_Y, lz = i / (RH_X * RH_Y);
+        const int x = bx0 + lx, y = by0 + ly, z = bz0 + lz;
+        float org = 0.f, post = 0.f, cm = -1.f;
+        if (x >= 0 && x < vx && y >= 0 && y < vy && z >= 0 && z < vz) {
+            const size_t v = x + (size_t)y * vx + (size_t)z * vx * vy;
+            float2 a = acc2[v];
+            if (!mask[v]) a = make_float2(0.f, 0.f);
+            if (!adaptive && a.y != 0.f) { a.x = a.x / a.y; a.y = 1.0f; }
+            org = recon[v];
+            float r = org + a.x * alpha;
+            if (flavor == 0) {
+                if ((double)r < (double)min_i * 0.9) r = (float)((double)min_i * 0.9);
+                if ((double)r > (double)max_i * 1.1) r = (float)((double)max_i * 1.1);
+            } else {
+                if (r < min_i * 0.9f) r = min_i * 0.9f;
+                if (r > max_i * 1.1f) r = max_i * 1.1f;
+            }
+            post = r; cm = a.y;
+            // the normalised accumulator is part of the interface (debug taps, adaptive mode): the tile's own voxels write it back
+            if (lx >= 1 && lx <= RT_X && ly >= 1 && ly <= RT_Y && lz >= 1 && lz <= RT_Z) acc2[v] = a;
+        }
+        s_org[lz][ly][lx] = org; s_post[lz][ly][lx] = post; s_cm[lz][ly][lx] = cm;
+    }
+    __syncthreads();
+    const float kreg = alpha * lambda / (delta * delta);
+    for (int i = threadIdx.x; i < RT_X * RT_Y * RT_Z; i += blockDim.x) {
+        const int lx = 1 + i % RT_X, ly = 1 + (i / RT_X) % RT_Y, lz = 1 + i / (RT_X * RT_Y);
+        const int x = bx0 + lx, y = by0 + ly, z = bz0 + lz;
+        if (x >= vx || y >= vy || z >= vz) continue;
+        const float cp = s_cm[lz][ly][lx], rp = s_post[lz][ly][lx], op = s_org[lz][ly][lx];
+        float val = 0.f, valW = 0.f, sum = 0.f;
+#pragma unroll
+        for (int d = 0; d < 13; ++d) {
+            const int dx = c_dirs[d][0], dy = c_dirs[d][1], dz = c_dirs[d][2];
+            const float f = 1.0f / (float)(abs(dx) + abs(dy) + abs(dz));
+            const float sf = sqrtf(f);
+            const float c2 = s_cm[lz + dz][ly + dy][lx + dx];
+            if (c2 < 0.f) continue;                       // pos2 outside the volume: neither term counts (cuda2.cu:2089-2093)
+            const float o2 = s_org[lz + dz][ly + dy][lx + dx];
+            {
+                float bi = 0.f;
+                if (!(cp <= 0.f || c2 <= 0.f)) {
+                    const float diff = (o2 - op) * sf / delta;
+                    bi = f / sqrtf(1.0f + diff * diff);
+                }
+                val += bi * s_post[lz + dz][ly + dy][lx + dx] * c2;
+                valW += bi * c2;
+                sum += bi;
+            }
+            const float c3 = s_cm[lz - dz][ly - dy][lx - dx];
+            if (c3 >= 0.f) {
+                float bi = 0.f;
+                if (!(c3 <= 0.f || c2 <= 0.f)) {          // AdaptiveRegularization1(i, pos3, pos2): cuda2.cu:2095
+                    const float diff = (o2 - s_org[lz - dz][ly - dy][lx - dx]) * sf / delta;
+                    bi = f / sqrtf(1.0f + diff * diff);
+                }
+                val += bi * s_post[lz - dz][ly - dy][lx - dx] * c3;
+                valW += bi * c3;
+                sum += bi;
+            }
+        }
+        val -= sum * rp * cp;
+        valW -= sum * cp;
+        val = rp * cp + kreg * val;
+        valW = cp + kreg * valW;
+        out[x + (size_t)y * vx + (size_t)z * vx * vy] = (valW > 0.0f) ? val / valW : 0.0f;
+    }
+}
+
 int svr_launch_regularize(svr_context* c, int adaptive, float alpha, float min_i, float max_i, float delta, float lambda)
 {
     ProfScope prof(c, 3);
-    reg_prep_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->recon, c->acc2, c->mask_u8, c->recon_tmp1, adaptive, alpha, min_i, max_i, c->flavor);
-    SVR_KERNEL_CHECK(c);
-    dim3 block(64, 4, 1), grid(divup_i(c->vx, 64), divup_i(c->vy, 4), c->vz);
-    reg_kernel<<<grid, block, 0, c->stream>>>(c->vx, c->vy, c->vz, c->recon, c->recon_tmp1, c->acc2, c->recon_tmp2, delta, alpha, lambda);
-    SVR_KERNEL_CHECK(c);
+    if (c->tune_regularize == 0) {
+        reg_prep_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->V, c->recon, c->acc2, c->mask_u8, c->recon_tmp1, adaptive, alpha, min_i, max_i, c->flavor);
+        SVR_KERNEL_CHECK(c);
+        dim3 block(64, 4, 1), grid(divup_i(c->vx, 64), divup_i(c->vy, 4), c->vz);
+        reg_kernel<<<grid, block, 0, c->stream>>>(c->vx, c->vy, c->vz, c->recon, c->recon_tmp1, c->acc2, c->recon_tmp2, delta, alpha, lambda);
+        SVR_KERNEL_CHECK(c);
+    } else {
+        dim3 grid(divup_i(c->vx, RT_X), divup_i(c->vy, RT_Y), divup_i(c->vz, RT_Z));
+        regularize_fused_kernel<<<grid, 256, 0, c->stream>>>(c->vx, c->vy, c->vz, c->recon, c->acc2, c->mask_u8, c->recon_tmp2, adaptive, alpha,
+                                                             min_i, max_i, delta, lambda, c->flavor);
+        SVR_KERNEL_CHECK(c);
+    }
     float* t = c->recon; c->recon = c->recon_tmp2; c->recon_tmp2 = t;
     return 0;
 }

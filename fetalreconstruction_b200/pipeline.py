@@ -94,8 +94,11 @@ class SVRPipeline:
     """State and steps of irtkReconstruction's GPU path for the slices [begin, end) of this rank."""
 
     def __init__(self, backend, S_global: int, begin: int, end: int, comm: Comm | None = None,
-                 params: SVRParams | None = None, accumulator_tensor=None):
+                 params: SVRParams | None = None, accumulator_tensor=None, host=None):
         self.b = backend
+        # the pure host helpers (slice-level EM, small-slice rule, M-step finish): by default the ones the C ABI exports
+        # (libsvr_b200.so); the CPU baseline arm of bench.py passes the oracle's own copies so that it never loads the GPU library
+        self.host = host if host is not None else R
         self.S = S_global
         self.begin, self.end = begin, end
         self.comm = comm or Comm()
@@ -161,7 +164,7 @@ class SVRPipeline:
         self._allreduce_accumulator()
         vn_local = self.b.gaussian_reconstruction_finish()
         voxel_num = self._gather(vn_local, np.int32)
-        self._small_slices = R.host_small_slices(voxel_num)
+        self._small_slices = self.host.host_small_slices(voxel_num)
         return voxel_num
 
     # -- SimulateSlicesGPU (irtkReconstructionGPU.cc:1163-1203) ------------------------------------
@@ -190,7 +193,7 @@ class SVRPipeline:
         pot = self._gather(pot_local)
         state = np.array([self._sigma_s, self._mix_s, self._mean_s, self._mean_s2, self._sigma_s2], np.float32)
         sw = self._slice_weight.astype(np.float32).copy()
-        R.host_slice_em(pot, self._scale, sw, np.asarray(self.p.force_excluded, np.int32), self._small_slices,
+        self.host.host_slice_em(pot, self._scale, sw, np.asarray(self.p.force_excluded, np.int32), self._small_slices,
                         self._step, state)
         self.slice_potential = pot
         self._slice_weight = sw
@@ -214,7 +217,7 @@ class SVRPipeline:
         sums = self.comm.sum(s5[:3].copy())
         mn = self.comm.min(s5[3:4].copy())
         mx = self.comm.max(s5[4:5].copy())
-        self._sigma, self._mix, self._m = R.mstep_finish(np.concatenate([sums, mn, mx]), it, self._step,
+        self._sigma, self._mix, self._m = self.host.mstep_finish(np.concatenate([sums, mn, mx]), it, self._step,
                                                          self._sigma, self._mix, self._m)
 
     def MaskVolumeGPU(self):

@@ -58,6 +58,28 @@ class PatchReconstruction:
     def launch_count(self):
         return int(self._lib.svr_launch_count(self._h))
 
+    # a PVR context is an svr_context with the PVR constants: stream, tuning and per-kernel timing are the SVR entry points
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._lib.svr_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._ck(self._lib.svr_synchronize(self._h))
+
+    def profile_enable(self, on=True):
+        self._ck(self._lib.svr_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._ck(self._lib.svr_profile_reset(self._h))
+
+    def profile_read(self):
+        from .reconstruction import Reconstruction
+        out = {}
+        for i, name in enumerate(Reconstruction.KERNEL_KINDS):
+            ms, n = C.c_double(), C.c_int64()
+            self._ck(self._lib.svr_profile_read(self._h, i, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     # ReconVolume<T>
     def recon_init(self, size, dim, recon_w2i, recon_i2w):
         sx, sy, sz = (int(v) for v in size)

@@ -72,7 +72,7 @@ class Reconstruction:
     def set_stream(self, cuda_stream_ptr: int | None):
         self._ck(self._lib.svr_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
-    TUNE_SCATTER, TUNE_SIMULATE = 0, 1
+    TUNE_SCATTER, TUNE_SIMULATE, TUNE_REGULARIZE = 0, 1, 2
 
     def set_tuning(self, key: int, value: int):
         """Kernel-variant selection for A/B measurements (svr_set_tuning)."""
@@ -85,7 +85,7 @@ class Reconstruction:
     def launch_count(self) -> int:
         return int(self._lib.svr_launch_count(self._h))
 
-    KERNEL_KINDS = ("gaussian", "simulate", "superres", "regularize", "em", "reg_eval")
+    KERNEL_KINDS = ("gaussian", "simulate", "superres", "regularize", "em", "reg_eval", "estep", "mstep", "scale", "robust_init")
 
     def profile_enable(self, on: bool = True):
         self._ck(self._lib.svr_profile_enable(self._h, int(on)))

@@ -54,8 +54,9 @@ enum {
     SVR_TUNE_SCATTER = 0,   /* K1 pass 2 / K3: 0 = paired per-lane reductions (default: fastest on every orientation measured,
                                profiles/r02_ww_ab.txt), 1 = warp windows + SIMT flush, 2 = warp windows + TMA reduce flush,
                                3 = paired for slices aligned with the volume axes and warp windows for the others */
-    SVR_TUNE_SIMULATE = 1   /* K2: 0 = per-tap loads + staged rows (default), 1 = TMA-staged windows for every tile,
+    SVR_TUNE_SIMULATE = 1,  /* K2: 0 = per-tap loads + staged rows (default), 1 = TMA-staged windows for every tile,
                                2 = windows for through-plane slices only */
+    SVR_TUNE_REGULARIZE = 2 /* K4 + K5: 0 = two kernels through L1/L2, 1 = one fused kernel with a shared-memory halo tile (default) */
 };
 int svr_set_tuning(svr_context *ctx, int key, int value);
 
@@ -229,9 +230,13 @@ enum svr_kernel_kind {
     SVR_K_SIMULATE = 1,   /* K2  simulate_kernel          */
     SVR_K_SUPERRES = 2,   /* K3  superres_scatter_kernel  */
     SVR_K_REGULARIZE = 3, /* K4+K5                        */
-    SVR_K_EM = 4,         /* E-step, M-step, scale, robust-init reductions */
+    SVR_K_EM = 4,         /* (round 1: all robust-statistics reductions; now split into the four kinds below) */
     SVR_K_REG_EVAL = 5,   /* reg_eval_kernel: fused sample + blur + NCC moments of the registration */
-    SVR_K_COUNT = 6
+    SVR_K_ESTEP = 6,      /* K7+K8 estep_kernel (+ potential_finish_kernel) */
+    SVR_K_MSTEP = 7,      /* K9 mstep_kernel (+ fold) */
+    SVR_K_SCALE = 8,      /* K10 scale_kernel (+ scale_finish_kernel) */
+    SVR_K_ROBUST_INIT = 9,/* K11 robust_init_kernel (+ fold) */
+    SVR_K_COUNT = 10
 };
 /* When enabled every launch of the kinds above is bracketed by a cudaEvent pair (no host sync). */
 int svr_profile_enable(svr_context *ctx, int on);

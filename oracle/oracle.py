@@ -192,6 +192,16 @@ def host_slice_em(slice_potential, scale, slice_weight, force_excluded, small_sl
                             _ptr(fe), C.c_int(fe.size), _ptr(sm), C.c_int(sm.size), C.c_double(step), _ptr(state5))
 
 
+def host_small_slices(voxel_num):
+    """irtkReconstructionGPU.cc:2714-2726 on per-slice counts (deviation D4): slices with fewer than 10 % of the median count."""
+    vn = np.asarray(voxel_num, np.int32)
+    if vn.size == 0:
+        return np.zeros(0, np.int32)
+    tmp = np.sort(vn)
+    mid = min(int(np.floor(tmp.size * 0.5 + 0.5)), tmp.size - 1)
+    return np.nonzero(vn < 0.1 * tmp[mid])[0].astype(np.int32)
+
+
 # ---- registration (oracle/reg_oracle.c) -------------------------------------------------------------
 def reg_gauss_kernel(sigma):
     half = np.zeros(32, np.float32)

@@ -8,7 +8,6 @@ super-resolution iterations, transformations fixed), on libsvr_b200.so or on the
 import os
 import sys
 import time
-from types import SimpleNamespace
 
 import numpy as np
 
@@ -17,21 +16,7 @@ sys.path.insert(0, ROOT)
 FIXTURE = os.path.join(ROOT, "tests", "golden", "c2_setup.npz")
 
 
-def load_setup(path=FIXTURE):
-    z = np.load(path)
-    idx = dict(line.split() for line in str(z["index"]).splitlines() if line.strip())
-    S, Nx, Ny = int(idx["S"]), int(idx["Nx"]), int(idx["Ny"])
-    vx, vy, vz, voxel = int(idx["vx"]), int(idx["vy"]), int(idx["vz"]), float(idx["voxel"])
-    from fetalreconstruction_b200.geometry import ImageAttributes
-    attrs = z["slice_attrs"].reshape(S, 18)
-    slice_attrs = [ImageAttributes(int(a[0]), int(a[1]), int(a[2]), a[3], a[4], a[5], a[6:9].copy(), a[9:12].copy(), a[12:15].copy(),
-                                   a[15:18].copy()) for a in attrs]
-    return SimpleNamespace(S=S, cfg=SimpleNamespace(vol_voxel=voxel, vol_size=(vx, vy, vz), name="C2"),
-                           slices=z["slices"].reshape(S, Ny, Nx), mask=z["mask"].reshape(vz, vy, vx), dims=z["dims"].reshape(S, 3),
-                           trans=z["T"].reshape(S, 16), trans_inv=z["Tinv"].reshape(S, 16), i2w=z["I2W"].reshape(S, 16),
-                           w2i=z["W2I"].reshape(S, 16), recon_i2w=z["recon_i2w"], recon_w2i=z["recon_w2i"],
-                           stack_index=z["stack_index"], stack_factor=z["stack_factor"], slice_attrs=slice_attrs,
-                           sizes=z["sizes"].reshape(S, 2))
+from fetalreconstruction_b200.fixtures import load_c2_setup as load_setup  # noqa: E402
 
 
 def run(arm, out=None, iterations=4):

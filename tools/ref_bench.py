@@ -50,7 +50,7 @@ class Timed:
         setattr(self._b, k, v)
 
 
-def run_arm(arm, out, rec_iters, timing_only=False):
+def run_arm(arm, out, rec_iters, timing_only=False, reps=3):
     import torch
     from fetalreconstruction_b200.pipeline import SVRPipeline, SVRParams, upload_dataset
     ds = torch.load(CACHE, weights_only=False)
@@ -72,22 +72,19 @@ def run_arm(arm, out, rec_iters, timing_only=False):
     setup_s = time.perf_counter() - t0
     if timing_only:
         # bench.py's reference_cuda leg: one untimed outer iteration (first-call costs of the process: module load, lazy
-        # allocations), then the timed one
-        # the reference allocates and frees three volumes in every Superresolution call, whose cost varies wildly from run to
-        # run (30 ms .. 800 ms per call seen on the same box): time three iterations and report the fastest
+        # allocations), then `reps` timed ones; the MEDIAN is reported (the reference allocates and frees three volumes in every
+        # Superresolution call, whose cost varies from run to run, so all timings are listed too)
         p.outer_iteration(0)
-        best = None
-        all_s = []
-        for _ in range(3):
+        runs = []
+        for _ in range(max(reps, 1)):
             b.times.clear()
             t0 = time.perf_counter()
             p.outer_iteration(0)
-            iter_s = time.perf_counter() - t0
-            all_s.append(iter_s)
-            if best is None or iter_s < best[0]:
-                best = (iter_s, {k: 1e3 * t / n for k, (t, n) in b.times.items()})
-        print("REFBENCH_JSON " + json.dumps({"arm": arm, "S": int(ds.S), "rec_iters": rec_iters, "iteration_s": best[0], "setup_s": setup_s,
-                                             "iterations_s": all_s, "ms_per_call": best[1]}))
+            runs.append((time.perf_counter() - t0, {k: 1e3 * t / n for k, (t, n) in b.times.items()}))
+        order = sorted(range(len(runs)), key=lambda i: runs[i][0])
+        med = runs[order[len(order) // 2]]
+        print("REFBENCH_JSON " + json.dumps({"arm": arm, "S": int(ds.S), "rec_iters": rec_iters, "iteration_s": med[0], "setup_s": setup_s,
+                                             "iterations_s": [r[0] for r in runs], "ms_per_call": med[1]}))
         return
     b.times.clear()
     res = {}
@@ -180,17 +177,24 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--rec-iters", type=int, default=2)
     ap.add_argument("--timing-only", action="store_true")
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--stack-list", default=None, help="gen: comma-separated stack numbers instead of the first --stacks")
     a = ap.parse_args()
     if a.arm == "gen":
         import torch
         from fetalreconstruction_b200.phantom import c3_config, make_dataset
-        ds = make_dataset(c3_config(), device="cuda" if torch.cuda.is_available() else "cpu", stacks=range(a.stacks))
-        torch.save(ds, CACHE)
+        if a.stack_list:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import ref_live
+            ds = ref_live.gen(CACHE, [int(v) for v in a.stack_list.split(",")])
+        else:
+            ds = make_dataset(c3_config(), device="cuda" if torch.cuda.is_available() else "cpu", stacks=range(a.stacks))
+            torch.save(ds, CACHE)
         print("generated", ds.S, "slices", ds.slices.shape)
     elif a.arm == "cmp":
         compare(*a.paths)
     else:
-        run_arm(a.arm, a.out, a.rec_iters, a.timing_only)
+        run_arm(a.arm, a.out, a.rec_iters, a.timing_only, a.reps)
 
 
 if __name__ == "__main__":
