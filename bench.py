@@ -290,10 +290,12 @@ def run_reference_cuda(cfg, reps=3):
         per = {}
         for st in range(cfg.n_stacks):
             ds_ = one(str(st), 1)
+            mc = ds_["ms_per_call"]
+            grp = lambda *keys: round(sum(mc.get(k, 0.0) for k in keys), 2)
             per[str(st)] = {"seconds_per_outer_iteration": round(ds_["iteration_s"], 4),
-                            "GaussianReconstruction_ms": round(ds_["ms_per_call"].get("GaussianReconstruction", ds_["ms_per_call"].get("gaussian_reconstruction_local", 0.0)), 2),
-                            "SimulateSlices_ms": round(ds_["ms_per_call"].get("SimulateSlices", 0.0), 2),
-                            "Superresolution_ms": round(ds_["ms_per_call"].get("Superresolution", ds_["ms_per_call"].get("superresolution_local", 0.0)), 2)}
+                            "GaussianReconstruction_ms": grp("GaussianReconstruction", "gaussian_reconstruction_local", "gaussian_reconstruction_finish"),
+                            "SimulateSlices_ms": grp("SimulateSlices"),
+                            "Superresolution_ms": grp("Superresolution", "superresolution_local", "superresolution_finish")}
         out["per_stack"] = per
     except Exception as e:
         out["per_stack"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
@@ -437,7 +439,7 @@ def bench_svr(args):
     from fetalreconstruction_b200.reconstruction import Reconstruction
 
     world, rank, local, dev, group = init_dist()
-    comm = Comm(group, dev)
+    comm = Comm(group, dev, stream_ordered=True)          # the library runs on the torch stream below (svr_set_stream)
     build.build()
 
     # Sharding: rank r takes every N-th slice (j % N == r) of EVERY stack, so all ranks see the same mix of stack
@@ -460,6 +462,7 @@ def bench_svr(args):
     with torch.cuda.stream(stream):
         backend = Reconstruction(local)
         backend.set_stream(stream.cuda_stream)
+        backend.set_async(True)                           # calls that return no host data only enqueue (svr_set_async)
         for key, val in args.tune:
             backend.set_tuning(key, val)
         upload_dataset(backend, ds)

@@ -30,6 +30,10 @@ _SIGNATURES = {
     "svr_synchronize": (ip, [vp]),
     "svr_launch_count": (C.c_int64, [vp]),
     "svr_set_tuning": (ip, [vp, ip, ip]),
+    "svr_get_stream": (ip, [vp, C.POINTER(vp)]),
+    "svr_set_async": (ip, [vp, ip]),
+    "svr_make_current": (ip, [vp]),
+    "svr_host_partition_strided": (ip, [ip, vp, ip, ip, vp, I]),
     "svr_init_reconstruction_volume": (ip, [vp, ip, ip, ip, fp, fp, fp, vp]),
     "svr_set_mask": (ip, [vp, ip, ip, ip, vp]),
     "svr_init_storage_volumes": (ip, [vp, ip, ip, ip]),

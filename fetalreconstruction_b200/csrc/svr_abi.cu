@@ -141,6 +141,29 @@ int svr_synchronize(svr_context* c)
     return 0;
 }
 
+int svr_get_stream(svr_context* c, void** cuda_stream)
+{
+    REQUIRE(c, c && cuda_stream, "svr_get_stream: NULL argument");
+    *cuda_stream = (void*)c->stream;
+    return 0;
+}
+
+int svr_set_async(svr_context* c, int on)
+{
+    SVR_ENTRY(c);
+    REQUIRE(c, c, "null context");
+    if (!on) SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->async = on != 0;
+    return 0;
+}
+
+int svr_make_current(svr_context* c)
+{
+    REQUIRE(c, c, "null context");
+    SVR_CUDA(c, cudaSetDevice(c->device));
+    return 0;
+}
+
 int64_t svr_launch_count(const svr_context* c) { return c ? c->launches : 0; }
 
 int svr_set_tuning(svr_context* c, int key, int value)
@@ -185,7 +208,7 @@ int svr_profile_reset(svr_context* c)
 static int upload(svr_context* c, void* dst, const void* src, size_t bytes)
 {
     SVR_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));   // the caller may free its buffer on return (reference semantics)
+    SVR_SYNC(c);                                     // the caller may free its buffer on return (reference semantics)
     return 0;
 }
 static int download(svr_context* c, void* dst, const void* src, size_t bytes)
@@ -217,7 +240,7 @@ int svr_init_reconstruction_volume(svr_context* c, int sx, int sy, int sz, float
     c->have_mask = false;
     if (int r = svr_window_build_maps(c)) return r;      // tensor-map menus over acc2 / pack2 (svr_window.cu)
     if (data) return upload(c, c->recon, data, c->V * sizeof(float));
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -358,7 +381,7 @@ int svr_update_scale_vector(svr_context* c, const float* scales, const float* sl
     SVR_CUDA(c, cudaMemcpyAsync(c->scales, scales, c->S * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SVR_CUDA(c, cudaMemcpyAsync(c->scales_mstep, scales, c->S * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SVR_CUDA(c, cudaMemcpyAsync(c->slice_weights, slice_weights, c->S * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -394,7 +417,7 @@ int svr_initialize_em_values(svr_context* c)
     REQUIRE(c, c, "null context");
     if (c->NP == 0) return 0;
     if (svr_launch_init_em(c)) return 1;
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -416,7 +439,7 @@ int svr_gaussian_reconstruction_local(svr_context* c)
     SVR_CUDA(c, cudaMemsetAsync(c->acc2, 0, c->V * sizeof(float2), c->stream));
     if (svr_launch_gaussian_scatter(c)) return 1;
     // the caller all-reduces the accumulator next, possibly on another stream: like every entry point, return when done
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -426,7 +449,7 @@ int svr_gaussian_reconstruction_finish(svr_context* c, int* voxel_num)
     if (int r = ready(c, "svr_gaussian_reconstruction")) return r;
     if (svr_launch_equalize(c)) return 1;
     if (voxel_num && c->S) return download(c, voxel_num, c->slice_count, c->S * sizeof(int));
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -449,7 +472,7 @@ int svr_simulate_slices(svr_context* c, unsigned char* slice_inside)
         for (int i = 0; i < c->S; ++i) slice_inside[i] = tmp[i] != 0;
         return 0;
     }
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -479,7 +502,7 @@ int svr_estep(svr_context* c, float m, float sigma, float mix, float* slice_pote
     if (c->NP == 0) return 0;
     if (svr_launch_estep(c, m, sigma, mix)) return 1;
     if (slice_potential) return download(c, slice_potential, c->slice_tmp, c->S * sizeof(float));
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -539,7 +562,7 @@ int svr_superresolution_local(svr_context* c, const float* slice_weight)
     if (slice_weight && c->S) if (int r = svr_update_slice_weights(c, slice_weight)) return r;
     SVR_CUDA(c, cudaMemsetAsync(c->acc2, 0, c->V * sizeof(float2), c->stream));
     if (svr_launch_superres_scatter(c)) return 1;
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));      // see svr_gaussian_reconstruction_local
+    SVR_SYNC(c);                                         // see svr_gaussian_reconstruction_local
     return 0;
 }
 
@@ -548,7 +571,7 @@ int svr_superresolution_finish(svr_context* c, int adaptive, float alpha, float 
     SVR_ENTRY(c);
     if (int r = ready(c, "svr_superresolution")) return r;
     if (svr_launch_regularize(c, adaptive, alpha, min_i, max_i, delta, lambda)) return 1;
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -566,7 +589,7 @@ int svr_mask_volume(svr_context* c)
     SVR_ENTRY(c);
     if (int r = ready(c, "svr_mask_volume")) return r;
     if (svr_launch_mask_volume(c)) return 1;
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -584,7 +607,7 @@ int svr_scale_volume_apply(svr_context* c, float scale)
     SVR_ENTRY(c);
     REQUIRE(c, c && c->recon, "svr_scale_volume: volume not initialised");
     if (svr_launch_scale_volume_apply(c, scale)) return 1;
-    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
+    SVR_SYNC(c);
     return 0;
 }
 
@@ -754,6 +777,20 @@ int svr_host_small_slices(int S, const int* voxel_num, int* out_small, int* n_ou
     const int median = tmp[mid];
     for (int i = 0; i < S; i++)
         if (voxel_num[i] < 0.1 * median) out_small[(*n_out)++] = i;
+    return 0;
+}
+
+int svr_host_partition_strided(int n_stacks, const int* slices_per_stack, int nranks, int rank, int* out_indices, int* out_count)
+{
+    if (n_stacks < 0 || nranks <= 0 || rank < 0 || rank >= nranks || !out_count || (n_stacks > 0 && (!slices_per_stack || !out_indices)))
+        return 2;
+    int n = 0, base = 0;
+    for (int st = 0; st < n_stacks; ++st) {
+        if (slices_per_stack[st] < 0) return 2;
+        for (int j = rank; j < slices_per_stack[st]; j += nranks) out_indices[n++] = base + j;
+        base += slices_per_stack[st];
+    }
+    *out_count = n;
     return 0;
 }
 

@@ -12,6 +12,7 @@ struct svr_context {
     cudaStream_t stream = nullptr;
     std::string err;
     long long launches = 0;
+    bool async = false;            // svr_set_async: entry points that return no host data do not wait for the stream
 
     // ---- volume side (V voxels) ----
     int vx = 0, vy = 0, vz = 0;
@@ -102,6 +103,11 @@ int svr_fail(svr_context* ctx, const char* what, cudaError_t e, const char* file
     do {                                                                           \
         cudaError_t _e = (call);                                                   \
         if (_e != cudaSuccess) return svr_fail((ctx), #call, _e, __FILE__, __LINE__); \
+    } while (0)
+// end of an entry point that returns no host data: wait for the stream unless the context is asynchronous
+#define SVR_SYNC(ctx)                                                              \
+    do {                                                                           \
+        if (!(ctx)->async) SVR_CUDA((ctx), cudaStreamSynchronize((ctx)->stream));   \
     } while (0)
 #define SVR_KERNEL_CHECK(ctx)                                                      \
     do {                                                                           \

@@ -43,9 +43,12 @@ class SVRParams:
 class Comm:
     """Thin wrapper over a torch.distributed process group (or nothing for one rank)."""
 
-    def __init__(self, group=None, device=None):
+    def __init__(self, group=None, device=None, stream_ordered=False):
+        """stream_ordered: the library runs on torch's current stream (svr_set_stream), so a collective issued through torch is
+        ordered with the library's kernels on the device and the host does not have to wait for it."""
         self.group = group
         self.device = device
+        self.stream_ordered = stream_ordered
         if group is not None:
             import torch.distributed as dist
             self.dist = dist
@@ -81,9 +84,21 @@ class Comm:
         the next library call can touch the buffer (a few microseconds when the streams are the same)."""
         if self.active:
             self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
-            if tensor.is_cuda:
+            if tensor.is_cuda and not self.stream_ordered:
                 import torch
                 torch.cuda.current_stream(tensor.device).synchronize()
+
+    def gather_rows(self, arr):
+        """Every rank's copy of a small host vector, stacked [size, n]: one collective for statistics that need different
+        reductions (the M-step's sums, minimum and maximum)."""
+        arr = np.ascontiguousarray(arr, np.float64)
+        if not self.active:
+            return arr[None]
+        import torch
+        t = torch.as_tensor(arr, device=self.device)
+        out = [torch.empty_like(t) for _ in range(self.size)]
+        self.dist.all_gather(out, t, group=self.group)
+        return torch.stack(out).cpu().numpy()
 
     def barrier(self):
         if self.active:
@@ -168,9 +183,15 @@ class SVRPipeline:
         return voxel_num
 
     # -- SimulateSlicesGPU (irtkReconstructionGPU.cc:1163-1203) ------------------------------------
-    def SimulateSlicesGPU(self):
-        inside = self.b.SimulateSlices()
-        self._slice_inside = self._gather(inside.astype(np.float64), np.float64) > 0
+    def SimulateSlicesGPU(self, need_inside=True):
+        """need_inside: fetch and exchange the per-slice "inside" flags (only InitializeRobustStatisticsGPU and the evaluation
+        listing read them: the inner loop skips the read-back and its tiny all-reduce)."""
+        try:
+            inside = self.b.SimulateSlices(fetch_inside=need_inside)
+        except TypeError:                                   # backend twins without the keyword (oracle / reference)
+            inside = self.b.SimulateSlices()
+        if need_inside:
+            self._slice_inside = self._gather(inside.astype(np.float64), np.float64) > 0
 
     # -- InitializeRobustStatisticsGPU (irtkReconstructionGPU.cc:2988-3020) ------------------------
     def InitializeRobustStatisticsGPU(self):
@@ -213,12 +234,9 @@ class SVRPipeline:
 
     # -- MStepGPU (irtkReconstructionGPU.cc:4214-4224) ---------------------------------------------
     def MStepGPU(self, it):
-        s5 = self.b.mstep_local()
-        sums = self.comm.sum(s5[:3].copy())
-        mn = self.comm.min(s5[3:4].copy())
-        mx = self.comm.max(s5[4:5].copy())
-        self._sigma, self._mix, self._m = self.host.mstep_finish(np.concatenate([sums, mn, mx]), it, self._step,
-                                                         self._sigma, self._mix, self._m)
+        rows = self.comm.gather_rows(self.b.mstep_local())       # one exchange; sums / min / max folded on the host
+        s5 = np.concatenate([rows[:, :3].sum(0), rows[:, 3:4].min(0), rows[:, 4:5].max(0)])
+        self._sigma, self._mix, self._m = self.host.mstep_finish(s5, it, self._step, self._sigma, self._mix, self._m)
 
     def MaskVolumeGPU(self):
         self.b.maskVolume()
@@ -246,7 +264,7 @@ class SVRPipeline:
         if self.p.intensity_matching:
             self.ScaleGPU()
         self.SuperresolutionGPU(i + 1)
-        self.SimulateSlicesGPU()
+        self.SimulateSlicesGPU(need_inside=False)
         self.MStepGPU(i + 1)
         self.EStepGPU()
 

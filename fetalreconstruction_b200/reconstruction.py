@@ -78,6 +78,10 @@ class Reconstruction:
         """Kernel-variant selection for A/B measurements (svr_set_tuning)."""
         self._ck(self._lib.svr_set_tuning(self._h, int(key), int(value)))
 
+    def set_async(self, on: bool = True):
+        """Entry points that return no host data only enqueue their work (svr_set_async)."""
+        self._ck(self._lib.svr_set_async(self._h, int(bool(on))))
+
     def synchronize(self):
         self._ck(self._lib.svr_synchronize(self._h))
 
@@ -175,8 +179,11 @@ class Reconstruction:
         self._ck(self._lib.svr_gaussian_reconstruction(self._h, _p(vn)))
         return vn[:self.S]
 
-    def SimulateSlices(self):
-        """Returns slice_inside (bool per slice)."""
+    def SimulateSlices(self, fetch_inside=True):
+        """Returns slice_inside (bool per slice), or None without the read-back (fetch_inside=False)."""
+        if not fetch_inside:
+            self._ck(self._lib.svr_simulate_slices(self._h, None))
+            return None
         si = np.zeros(max(self.S, 1), np.uint8)
         self._ck(self._lib.svr_simulate_slices(self._h, _p(si)))
         return si[:self.S].astype(bool)
@@ -379,6 +386,17 @@ def host_small_slices(voxel_num):
     n = C.c_int()
     if lib.svr_host_small_slices(int(vn.size), _p(vn), _p(out), C.byref(n)) != 0:
         raise SVRError("svr_host_small_slices: bad argument")
+    return out[:n.value].copy()
+
+
+def host_partition_strided(slices_per_stack, nranks, rank):
+    """Indices (stack-major global order) of the slices of `rank`: every nranks-th slice of every stack."""
+    lib = _lib.load()
+    sps = np.ascontiguousarray(slices_per_stack, np.int32)
+    out = np.zeros(max(int(sps.sum()), 1), np.int32)
+    n = C.c_int()
+    if lib.svr_host_partition_strided(int(sps.size), _p(sps), int(nranks), int(rank), _p(out), C.byref(n)) != 0:
+        raise SVRError("svr_host_partition_strided: bad argument")
     return out[:n.value].copy()
 
 

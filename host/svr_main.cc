@@ -109,7 +109,7 @@ void usage()
         "  --rec_iterations_last arg (=13)    Number of superresolution iterations for the last iteration\n"
         "  --num_stacks_tuner arg (=0)        Use only the first x input stacks\n"
         "  --no_log arg (=0)                  Do not redirect cout and cerr to log files.\n"
-        "  -d [ --devices ] arg               GPU to use (one device per process; ranks are launched one per GPU)\n"
+        "  -d [ --devices ] arg               GPUs to use, e.g. -d 0 1 2 3: one rank per device, slices sharded, NCCL all-reduce\n"
         "  --tfolder arg                      Use existing slice-to-volume transformations to initialize the reconstruction.\n"
         "  --referenceVolume arg              Optional reference volume used as inital reconstruction.\n"
         "  --useCPU / --useCPUReg / --useGPUReg / --useAutoTemplate / --disableBiasCorrection / --useNMI\n"
@@ -268,9 +268,10 @@ int main(int argc, char** argv)
         stack_transformations.push_back(r);
     }
 
-    const int device = o.devices.empty() ? 0 : o.devices[0];
-    if (o.devices.size() > 1) std::cout << "NOTE: one process drives one GPU; using device " << device << " (launch one rank per GPU for more)." << std::endl;
-    svr::Reconstruction reconstruction(device);
+    // -d d0 d1 ...: one rank per device (one host thread each), slices sharded, NCCL all-reduce of the volume accumulator
+    // (reference: reconstruction.cc:355-386 hands the device list to class Reconstruction, cuda2.cu:616-706)
+    svr::Reconstruction reconstruction(o.devices.empty() ? std::vector<int>(1, 0) : o.devices);
+    if (o.devices.size() > 1) std::cout << "Using " << o.devices.size() << " GPUs (one rank per device)." << std::endl;
     reconstruction.debug = o.debug || o.debug_gpu;
     for (auto& t : stack_transformations) t.invert();          // InvertStackTransformations, irtkReconstructionGPU.cc:5308-5317
 

@@ -9,27 +9,106 @@
 #include <cstdlib>
 #include <iostream>
 #include <stdexcept>
+#include <thread>
+#ifdef SVR_WITH_NCCL
+#include <nccl.h>
+#endif
 
 namespace svr {
 
-Reconstruction::Reconstruction(int device) : device_(device) {}
+Reconstruction::Reconstruction(int device) : devices_(1, device) {}
+Reconstruction::Reconstruction(const std::vector<int>& devices) : devices_(devices.empty() ? std::vector<int>(1, 0) : devices) {}
 
-// The device context is created on the first device call (SyncGPU): the stack/mask/slice set-up above it is host work
+// The device contexts are created on the first device call (SyncGPU): the stack/mask/slice set-up above it is host work
 // and can be run (and tested) on a machine without a GPU; everything from SyncGPU on fails loudly without one.
 void Reconstruction::ensure_context()
 {
-    if (c_) return;
-    if (svr_create(&c_, device_) != 0) throw std::runtime_error(std::string("svr_create: ") + svr_last_error(nullptr));
+    if (!ranks_.empty()) return;
+    ranks_.resize(devices_.size());
+    for (size_t r = 0; r < devices_.size(); ++r) {
+        ranks_[r].device = devices_[r];
+        if (svr_create(&ranks_[r].c, devices_[r]) != 0) throw std::runtime_error(std::string("svr_create: ") + svr_last_error(nullptr));
+        if (svr_get_stream(ranks_[r].c, &ranks_[r].stream) != 0) throw std::runtime_error("svr_get_stream failed");
+    }
+    c_ = ranks_[0].c;
+    if (ranks_.size() > 1) {
+#ifdef SVR_WITH_NCCL
+        std::vector<ncclComm_t> comms(ranks_.size());
+        const ncclResult_t rc = ncclCommInitAll(comms.data(), (int)ranks_.size(), devices_.data());
+        if (rc != ncclSuccess) throw std::runtime_error(std::string("ncclCommInitAll: ") + ncclGetErrorString(rc));
+        for (size_t r = 0; r < ranks_.size(); ++r) ranks_[r].comm = comms[r];
+        // between *_local and *_finish the all-reduce is enqueued on the context's stream: no host round trip is needed
+        for (Rank& r : ranks_) svr_set_async(r.c, 1);
+        std::cout << "NCCL: " << ranks_.size() << " ranks (one per GPU), all-reduce of the volume accumulator over NVLink" << std::endl;
+#else
+        throw std::runtime_error("more than one device requested, but this binary was built without NCCL (nccl.h not found at build time)");
+#endif
+    }
 }
 
 Reconstruction::~Reconstruction()
 {
-    if (c_) svr_destroy(c_);
+    for (Rank& r : ranks_) {
+#ifdef SVR_WITH_NCCL
+        if (r.comm) ncclCommDestroy((ncclComm_t)r.comm);
+#endif
+        if (r.c) svr_destroy(r.c);
+    }
 }
 
 void Reconstruction::ck(int rc, const char* what) const
 {
     if (rc != 0) throw std::runtime_error(std::string(what) + ": " + svr_last_error(c_));
+}
+
+// Runs f(rank) for every rank: inline for one rank, one host thread per rank otherwise (each makes its device current: the
+// library calls carry a device guard of their own, the NCCL call next to them needs the right current device).
+template <class F>
+void Reconstruction::each_rank(F&& f)
+{
+    if (ranks_.size() == 1) { f(ranks_[0]); return; }
+    std::vector<std::thread> th;
+    std::vector<std::string> err(ranks_.size());
+    for (size_t i = 0; i < ranks_.size(); ++i)
+        th.emplace_back([&, i] {
+            try {
+                if (svr_make_current(ranks_[i].c) != 0) throw std::runtime_error(svr_last_error(ranks_[i].c));
+                f(ranks_[i]);
+            } catch (const std::exception& e) { err[i] = e.what()[0] ? e.what() : "error"; }
+        });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < err.size(); ++i)
+        if (!err[i].empty()) throw std::runtime_error("rank " + std::to_string(i) + " (device " + std::to_string(ranks_[i].device) + "): " + err[i]);
+}
+
+// this rank's share of a per-slice vector (stride values per slice) / the way back
+template <class T>
+std::vector<T> Reconstruction::take(const Rank& r, const std::vector<T>& global, int stride) const
+{
+    std::vector<T> out(r.idx.size() * (size_t)stride);
+    for (size_t j = 0; j < r.idx.size(); ++j)
+        for (int q = 0; q < stride; ++q) out[j * stride + q] = global[(size_t)r.idx[j] * stride + q];
+    return out;
+}
+template <class T>
+void Reconstruction::put(const Rank& r, const std::vector<T>& local, std::vector<T>& global, int stride) const
+{
+    for (size_t j = 0; j < r.idx.size(); ++j)
+        for (int q = 0; q < stride; ++q) global[(size_t)r.idx[j] * stride + q] = local[j * stride + q];
+}
+
+// Sum of the interleaved {numerator, denominator} accumulator over the ranks, in place, on the context's stream.
+void Reconstruction::allreduce_accumulator(Rank& r)
+{
+    if (ranks_.size() == 1) return;
+#ifdef SVR_WITH_NCCL
+    void* buf = nullptr; size_t bytes = 0;
+    if (svr_device_buffer(r.c, SVR_BUF_ACCUMULATOR, &buf, &bytes) != 0) throw std::runtime_error(svr_last_error(r.c));
+    const ncclResult_t rc = ncclAllReduce(buf, buf, bytes / sizeof(float), ncclFloat, ncclSum, (ncclComm_t)r.comm, (cudaStream_t)r.stream);
+    if (rc != ncclSuccess) throw std::runtime_error(std::string("ncclAllReduce: ") + ncclGetErrorString(rc));
+#else
+    (void)r;
+#endif
 }
 
 double Reconstruction::device_ms(int kind, long long* launches) const
@@ -40,7 +119,7 @@ double Reconstruction::device_ms(int kind, long long* launches) const
     return ms;
 }
 
-void Reconstruction::profile(bool on) { ensure_context(); svr_profile_enable(c_, on ? 1 : 0); }
+void Reconstruction::profile(bool on) { ensure_context(); for (Rank& r : ranks_) svr_profile_enable(r.c, on ? 1 : 0); }
 
 // Writes what SyncGPU / UpdateGPUTranformationMatrices would upload, as raw little-endian arrays plus a text index, so
 // the same inputs can be fed to other backends (tools/c2_parity.py drives the reference's CUDA path with them).
@@ -258,6 +337,8 @@ void Reconstruction::SaveTransformations(const std::string& prefix)
 }
 
 // ---- SyncGPU, irtkReconstructionGPU.cc:249-328 ---------------------------------------------------------------------
+#define RCK(r, call, what) do { if ((call) != 0) throw std::runtime_error(std::string(what) + ": " + svr_last_error((r).c)); } while (0)
+
 void Reconstruction::SyncGPU()
 {
     std::cout << "SyncGPU()" << std::endl;
@@ -265,10 +346,8 @@ void Reconstruction::SyncGPU()
     const ImageAttr& ra = reconstructed_.a;
     std::vector<float> vol(reconstructed_.n());
     for (size_t i = 0; i < vol.size(); ++i) vol[i] = (float)reconstructed_.v[i];
-    ck(svr_init_reconstruction_volume(c_, ra.x, ra.y, ra.z, (float)ra.dx, (float)ra.dy, (float)ra.dz, vol.data()), "InitReconstructionVolume");
     std::vector<float> mask(mask_.n());
     for (size_t i = 0; i < mask.size(); ++i) mask[i] = (float)mask_.v[i];
-    ck(svr_set_mask(c_, mask_.a.x, mask_.a.y, mask_.a.z, mask.data()), "setMask");
 
     int minx = INT_MAX, miny = INT_MAX;
     Nx_ = Ny_ = 0;
@@ -280,18 +359,37 @@ void Reconstruction::SyncGPU()
     const double waste = ((double)(Nx_ - minx) * (Ny_ - miny) * S) * sizeof(double) * 5.0 / 1024.0;
     std::printf("GPU memory waste approx: %f KB with %d %d %d %d\n", waste, Nx_, Ny_, minx, miny);
 
-    ck(svr_init_storage_volumes(c_, Nx_, Ny_, S), "initStorageVolumes");
-    std::vector<float> cube((size_t)Nx_ * Ny_ * S, -1.0f);       // top-left aligned, pre-filled with the padding value
-    std::vector<int> sx(S), sy(S);
-    std::vector<float> dims(3 * (size_t)S);
+    // which slices go where: every D-th slice of every stack (svr_host_partition_strided)
+    std::vector<int> per_stack;
     for (int n = 0; n < S; ++n) {
-        const Image& s = slices_[n];
-        for (int y = 0; y < s.a.y; ++y) for (int x = 0; x < s.a.x; ++x) cube[((size_t)n * Ny_ + y) * Nx_ + x] = (float)s.at(x, y, 0);
-        sx[n] = s.a.x; sy[n] = s.a.y;
-        dims[3 * n] = (float)s.a.dx; dims[3 * n + 1] = (float)s.a.dy; dims[3 * n + 2] = (float)s.a.dz;
+        if (stack_index_[n] >= (int)per_stack.size()) per_stack.resize(stack_index_[n] + 1, 0);
+        per_stack[stack_index_[n]]++;
     }
-    ck(svr_fill_slices(c_, cube.data(), sx.data(), sy.data()), "FillSlices");
-    ck(svr_set_slice_dims(c_, dims.data(), 1.0f), "setSliceDims");
+    for (size_t r = 0; r < ranks_.size(); ++r) {
+        ranks_[r].idx.assign(std::max(S, 1), 0);
+        int n = 0;
+        ck(svr_host_partition_strided((int)per_stack.size(), per_stack.data(), (int)ranks_.size(), (int)r, ranks_[r].idx.data(), &n), "partition");
+        ranks_[r].idx.resize(n);
+        if (ranks_.size() > 1) std::cout << "rank " << r << " (device " << ranks_[r].device << "): " << n << " slices" << std::endl;
+    }
+    each_rank([&](Rank& r) {
+        RCK(r, svr_init_reconstruction_volume(r.c, ra.x, ra.y, ra.z, (float)ra.dx, (float)ra.dy, (float)ra.dz, vol.data()), "InitReconstructionVolume");
+        RCK(r, svr_set_mask(r.c, mask_.a.x, mask_.a.y, mask_.a.z, mask.data()), "setMask");
+        const int Sl = (int)r.idx.size();
+        RCK(r, svr_init_storage_volumes(r.c, Nx_, Ny_, Sl), "initStorageVolumes");
+        std::vector<float> cube((size_t)Nx_ * Ny_ * std::max(Sl, 1), -1.0f);       // top-left aligned, pre-filled with the padding value
+        std::vector<int> sx(std::max(Sl, 1)), sy(std::max(Sl, 1));
+        std::vector<float> dims(3 * (size_t)std::max(Sl, 1));
+        for (int j = 0; j < Sl; ++j) {
+            const Image& s = slices_[r.idx[j]];
+            for (int y = 0; y < s.a.y; ++y) for (int x = 0; x < s.a.x; ++x) cube[((size_t)j * Ny_ + y) * Nx_ + x] = (float)s.at(x, y, 0);
+            sx[j] = s.a.x; sy[j] = s.a.y;
+            dims[3 * j] = (float)s.a.dx; dims[3 * j + 1] = (float)s.a.dy; dims[3 * j + 2] = (float)s.a.dz;
+        }
+        RCK(r, svr_fill_slices(r.c, cube.data(), sx.data(), sy.data()), "FillSlices");
+        RCK(r, svr_set_slice_dims(r.c, dims.data(), 1.0f), "setSliceDims");
+        RCK(r, svr_synchronize(r.c), "synchronize");
+    });
     scale_.assign(S, 1.0f);
     slice_weight_.assign(S, 1.0f);
     slice_potential_.assign(S, 0.0f);
@@ -313,7 +411,10 @@ void Reconstruction::UpdateGPUTranformationMatrices()
     float ri2w[16], rw2i[16];
     reconstructed_.a.image_to_world().to_float16(ri2w);
     reconstructed_.a.world_to_image().to_float16(rw2i);
-    ck(svr_set_slice_matrices(c_, T.data(), Ti.data(), I2W.data(), W2I.data(), ri2w, rw2i), "SetSliceMatrices");
+    each_rank([&](Rank& r) {
+        const std::vector<float> t = take(r, T, 16), ti = take(r, Ti, 16), a = take(r, I2W, 16), b = take(r, W2I, 16);
+        RCK(r, svr_set_slice_matrices(r.c, t.data(), ti.data(), a.data(), b.data(), ri2w, rw2i), "SetSliceMatrices");
+    });
 }
 
 // ---- generatePSFVolume, irtkReconstructionGPU.cc:1496-1610: only the PSF image attributes reach the device -----------
@@ -325,7 +426,7 @@ void Reconstruction::generatePSFVolume()
     const int size[3] = { 128, 128, 128 };
     float i2w[16];
     attr.image_to_world().to_float16(i2w);
-    ck(svr_generate_psf_volume(c_, size, i2w, 1.0f), "generatePSFVolume");
+    for (Rank& r : ranks_) RCK(r, svr_generate_psf_volume(r.c, size, i2w, 1.0f), "generatePSFVolume");
 }
 
 // ---- InitializeEMGPU / InitializeEMValuesGPU, irtkReconstructionGPU.cc:2905-2953 -------------------------------------
@@ -333,8 +434,11 @@ void Reconstruction::InitializeEMValuesGPU()
 {
     std::fill(slice_weight_.begin(), slice_weight_.end(), 1.0f);
     std::fill(scale_.begin(), scale_.end(), 1.0f);
-    ck(svr_update_scale_vector(c_, scale_.data(), slice_weight_.data()), "UpdateScaleVector");
-    ck(svr_initialize_em_values(c_), "InitializeEMValues");
+    each_rank([&](Rank& r) {
+        const std::vector<float> sc = take(r, scale_), sw = take(r, slice_weight_);
+        RCK(r, svr_update_scale_vector(r.c, sc.data(), sw.data()), "UpdateScaleVector");
+        RCK(r, svr_initialize_em_values(r.c), "InitializeEMValues");
+    });
 }
 
 void Reconstruction::InitializeEMGPU()
@@ -350,7 +454,13 @@ void Reconstruction::GaussianReconstructionGPU()
     std::cout << "Gaussian reconstruction ... ";
     const int S = (int)slices_.size();
     std::vector<int> voxel_num(std::max(S, 1));
-    ck(svr_gaussian_reconstruction(c_, voxel_num.data()), "GaussianReconstruction");
+    each_rank([&](Rank& r) {
+        std::vector<int> vn(std::max<size_t>(r.idx.size(), 1));
+        RCK(r, svr_gaussian_reconstruction_local(r.c), "GaussianReconstruction");
+        allreduce_accumulator(r);                       // C1: numerator / denominator of the PSF-weighted splat
+        RCK(r, svr_gaussian_reconstruction_finish(r.c, vn.data()), "GaussianReconstruction");
+        put(r, vn, voxel_num);
+    });
     std::cout << "done." << std::endl;
     small_slices_.assign(std::max(S, 1), 0);
     int n = 0;
@@ -366,13 +476,22 @@ void Reconstruction::GaussianReconstructionGPU()
 // ---- SimulateSlicesGPU, irtkReconstructionGPU.cc:1163-1203 ----------------------------------------------------------
 void Reconstruction::SimulateSlicesGPU()
 {
-    ck(svr_simulate_slices(c_, slice_inside_.data()), "SimulateSlices");
+    each_rank([&](Rank& r) {
+        std::vector<unsigned char> in(std::max<size_t>(r.idx.size(), 1));
+        RCK(r, svr_simulate_slices(r.c, in.data()), "SimulateSlices");
+        put(r, in, slice_inside_);
+    });
 }
 
 // ---- InitializeRobustStatisticsGPU, irtkReconstructionGPU.cc:2988-3020 ----------------------------------------------
 void Reconstruction::InitializeRobustStatisticsGPU()
 {
-    ck(svr_initialize_robust_statistics(c_, &sigma_), "InitializeRobustStatistics");
+    // C4: the partial sums of the ranks are added on the host (one process drives all ranks: no collective is needed)
+    std::vector<double> part(2 * ranks_.size(), 0.0);
+    each_rank([&](Rank& r) { RCK(r, svr_initialize_robust_statistics_local(r.c, &part[2 * (&r - ranks_.data())]), "InitializeRobustStatistics"); });
+    double s0 = 0, s1 = 0;
+    for (size_t r = 0; r < ranks_.size(); ++r) { s0 += part[2 * r]; s1 += part[2 * r + 1]; }
+    sigma_ = (float)s0 / (float)s1;                 // _sigma = sa / sb, cuda2.cu:2305
     for (size_t i = 0; i < slices_.size(); ++i) if (!slice_inside_[i]) slice_weight_[i] = 0;
     for (int i : force_excluded_) if (i >= 0 && (size_t)i < slice_weight_.size()) slice_weight_[i] = 0;
     state5_[0] = 0.025f;                           // sigma_s
@@ -380,53 +499,94 @@ void Reconstruction::InitializeRobustStatisticsGPU()
     state5_[1] = 0.9f;                             // mix_s
     m_ = (float)(1.0f / (2.1f * max_intensity_ - 1.9f * min_intensity_));
     if (debug) std::cout << "Initializing robust statistics GPU: sigma=" << std::sqrt(sigma_) << " m=" << m_ << " mix=" << mix_ << " mix_s=" << state5_[1] << std::endl;
-    ck(svr_update_scale_vector(c_, scale_.data(), slice_weight_.data()), "UpdateScaleVector");
+    each_rank([&](Rank& r) {
+        const std::vector<float> sc = take(r, scale_), sw = take(r, slice_weight_);
+        RCK(r, svr_update_scale_vector(r.c, sc.data(), sw.data()), "UpdateScaleVector");
+    });
 }
 
 // ---- EStepGPU, irtkReconstructionGPU.cc:3162-3440 (device part + host slice-level EM) --------------------------------
 void Reconstruction::EStepGPU()
 {
     const int S = (int)slices_.size();
-    ck(svr_estep(c_, m_, sigma_, mix_, slice_potential_.data()), "EStep");
+    each_rank([&](Rank& r) {
+        std::vector<float> pot(std::max<size_t>(r.idx.size(), 1));
+        RCK(r, svr_estep(r.c, m_, sigma_, mix_, pot.data()), "EStep");
+        put(r, pot, slice_potential_);
+    });
     ck(svr_host_slice_em(S, slice_potential_.data(), scale_.data(), slice_weight_.data(), force_excluded_.data(), (int)force_excluded_.size(),
                          small_slices_.data(), (int)small_slices_.size(), step_, state5_), "slice EM");
-    ck(svr_update_slice_weights(c_, slice_weight_.data()), "UpdateSliceWeights");
+    each_rank([&](Rank& r) {
+        const std::vector<float> sw = take(r, slice_weight_);
+        RCK(r, svr_update_slice_weights(r.c, sw.data()), "UpdateSliceWeights");
+    });
 }
 
 // ---- ScaleGPU, irtkReconstructionGPU.cc:3751-3765 -------------------------------------------------------------------
 void Reconstruction::ScaleGPU()
 {
-    ck(svr_calculate_scale_vector(c_, scale_.data()), "CalculateScaleVector");
+    each_rank([&](Rank& r) {
+        std::vector<float> sc(std::max<size_t>(r.idx.size(), 1));
+        RCK(r, svr_calculate_scale_vector(r.c, sc.data()), "CalculateScaleVector");
+        put(r, sc, scale_);
+    });
 }
 
 // ---- SuperresolutionGPU, irtkReconstructionGPU.cc:4024-4053 ---------------------------------------------------------
 void Reconstruction::SuperresolutionGPU(int iter)
 {
-    ck(svr_superresolution(c_, iter, slice_weight_.data(), adaptive_ ? 1 : 0, (float)alpha_, (float)min_intensity_, (float)max_intensity_,
-                           (float)delta_, (float)lambda_), "Superresolution");
+    (void)iter;
+    each_rank([&](Rank& r) {
+        const std::vector<float> sw = take(r, slice_weight_);
+        RCK(r, svr_superresolution_local(r.c, sw.data()), "Superresolution");
+        allreduce_accumulator(r);                       // C2: addon / confidence map; every rank then regularises its replica (no C3 broadcast)
+        RCK(r, svr_superresolution_finish(r.c, adaptive_ ? 1 : 0, (float)alpha_, (float)min_intensity_, (float)max_intensity_, (float)delta_,
+                                          (float)lambda_), "Superresolution");
+    });
 }
 
 // ---- MStepGPU, irtkReconstructionGPU.cc:4214-4224 -------------------------------------------------------------------
 void Reconstruction::MStepGPU(int iter)
 {
-    ck(svr_mstep(c_, iter, (float)step_, &sigma_, &mix_, &m_), "MStep");
+    std::vector<double> part(5 * ranks_.size(), 0.0);
+    each_rank([&](Rank& r) { RCK(r, svr_mstep_local(r.c, &part[5 * (&r - ranks_.data())]), "MStep"); });
+    double s5[5] = { 0, 0, 0, 0, 0 };               // sums; min / max are seeded with 0 by the kernel (cuda2.cu:3103,3110)
+    for (size_t r = 0; r < ranks_.size(); ++r) {
+        for (int q = 0; q < 3; ++q) s5[q] += part[5 * r + q];
+        s5[3] = std::min(s5[3], part[5 * r + 3]);
+        s5[4] = std::max(s5[4], part[5 * r + 4]);
+    }
+    ck(svr_mstep_finish(s5, iter, (float)step_, &sigma_, &mix_, &m_), "MStep");
     if (debug) std::cout << "Voxel-wise robust statistics parameters GPU: sigma = " << std::sqrt(sigma_) << " mix = " << mix_ << " m = " << m_ << std::endl;
 }
 
-void Reconstruction::MaskVolumeGPU() { ck(svr_mask_volume(c_), "maskVolume"); }
-void Reconstruction::ScaleVolumeGPU() { ck(svr_scale_volume(c_, nullptr), "ScaleVolume"); }
+void Reconstruction::MaskVolumeGPU() { each_rank([&](Rank& r) { RCK(r, svr_mask_volume(r.c), "maskVolume"); }); }
+
+void Reconstruction::ScaleVolumeGPU()
+{
+    std::vector<double> part(2 * ranks_.size(), 0.0);
+    each_rank([&](Rank& r) { RCK(r, svr_scale_volume_local(r.c, &part[2 * (&r - ranks_.data())]), "ScaleVolume"); });
+    double s0 = 0, s1 = 0;
+    for (size_t r = 0; r < ranks_.size(); ++r) { s0 += part[2 * r]; s1 += part[2 * r + 1]; }
+    const float scale = (float)(s0 / s1);          // cuda2.cu:3459
+    each_rank([&](Rank& r) { RCK(r, svr_scale_volume_apply(r.c, scale), "ScaleVolume"); });
+}
 
 // ---- RestoreSliceIntensitiesGPU, irtkReconstructionGPU.cc:1026-1032 -------------------------------------------------
 void Reconstruction::RestoreSliceIntensitiesGPU()
 {
-    ck(svr_restore_slice_intensities(c_, stack_factor_.data(), (int)stack_factor_.size(), stack_index_.data()), "RestoreSliceIntensities");
+    each_rank([&](Rank& r) {
+        const std::vector<int> si = take(r, stack_index_);
+        if (si.empty()) return;
+        RCK(r, svr_restore_slice_intensities(r.c, stack_factor_.data(), (int)stack_factor_.size(), si.data()), "RestoreSliceIntensities");
+    });
 }
 
 // ---- SyncCPU, irtkReconstructionGPU.cc:2675-2683 --------------------------------------------------------------------
 void Reconstruction::SyncCPU()
 {
     std::vector<float> vol(reconstructed_.n());
-    ck(svr_sync_cpu(c_, vol.data()), "syncCPU");
+    ck(svr_sync_cpu(c_, vol.data()), "syncCPU");        // every rank holds the same replica: rank 0's is read
     for (size_t i = 0; i < vol.size(); ++i) reconstructed_.v[i] = vol[i];
 }
 
@@ -476,7 +636,6 @@ void Reconstruction::PrepareRegistrationSlices()
     }
     const double waste = ((double)(regW_ - minx) * (regH_ - miny) * S) * sizeof(double) * 5.0 / 1024.0;
     std::printf("GPU memory waste approx RegSlices: %f KB with %d %d %d %d\n", waste, regW_, regH_, minx, miny);
-    ck(svr_reg_init_storage(c_, regW_, regH_, S, (float)d, (float)d, (float)d), "initRegStorageVolumes");
     std::vector<double> m(12 * (size_t)S);
     std::vector<int> in_sizes(2 * (size_t)S), out_sizes(2 * (size_t)S);
     std::vector<float> i2w(16 * (size_t)S);
@@ -487,8 +646,16 @@ void Reconstruction::PrepareRegistrationSlices()
         out_sizes[2 * n] = res_attrs_[n].x; out_sizes[2 * n + 1] = res_attrs_[n].y;
         res_attrs_[n].image_to_world().to_float16(&i2w[16 * n]);
     }
-    ck(svr_reg_resample_slices(c_, m.data(), in_sizes.data(), out_sizes.data(), i2w.data()), "resampleRegSlices");
-    if (debug && S > 0) {
+    each_rank([&](Rank& r) {                          // every rank resamples (and later registers) its own slices: no exchange
+        const int Sl = (int)r.idx.size();
+        RCK(r, svr_reg_init_storage(r.c, regW_, regH_, Sl, (float)d, (float)d, (float)d), "initRegStorageVolumes");
+        if (Sl == 0) return;
+        const std::vector<double> ml = take(r, m, 12);
+        const std::vector<int> is = take(r, in_sizes, 2), os = take(r, out_sizes, 2);
+        const std::vector<float> il = take(r, i2w, 16);
+        RCK(r, svr_reg_resample_slices(r.c, ml.data(), is.data(), os.data(), il.data()), "resampleRegSlices");
+    });
+    if (debug && S > 0 && ranks_.size() == 1) {
         std::vector<float> cube((size_t)regW_ * regH_ * S);
         ck(svr_reg_debug_get(c_, 0, cube.data()), "debugRegSlices");
         // the device resamples the float32 slices it was given, the host form its double copies: up to one float ulp apart
@@ -520,9 +687,15 @@ void Reconstruction::SliceToVolumeRegistrationGPU()
         (transformations_[i].matrix() * mo).to_float16(&transf[16 * i]);
         a.image_to_world().to_float16(&ofs[16 * i]);
     }
-    ck(svr_reg_update_slices_i2w(c_, ofs.data()), "updateResampledSlicesI2W");
-    ck(svr_reg_prepare(c_), "prepareSliceToVolumeReg");
-    ck(svr_reg_register(c_, transf.data()), "registerSlicesToVolume");
+    each_rank([&](Rank& r) {
+        if (r.idx.empty()) return;
+        const std::vector<float> ol = take(r, ofs, 16);
+        std::vector<float> tl = take(r, transf, 16);
+        RCK(r, svr_reg_update_slices_i2w(r.c, ol.data()), "updateResampledSlicesI2W");
+        RCK(r, svr_reg_prepare(r.c), "prepareSliceToVolumeReg");
+        RCK(r, svr_reg_register(r.c, tl.data()), "registerSlicesToVolume");
+        put(r, tl, transf, 16);
+    });
     for (size_t i = 0; i < S; ++i) {
         const Mat4 mat = Mat4::from_float16(&transf[16 * i]) * mos[i].inverse();
         transformations_[i] = Rigid::from_matrix(mat);

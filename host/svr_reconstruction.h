@@ -21,10 +21,24 @@
 
 namespace svr {
 
+// One rank = one GPU = one svr_context holding a share of the slices and a full replica of the volume
+// (replaces class GPUWorker + the per-device vectors of class Reconstruction, GPUWorker.cpp:104-257, .cuh:103-139).
+struct Rank {
+    int device = 0;
+    svr_context* c = nullptr;
+    std::vector<int> idx;            // global indices of this rank's slices (svr_host_partition_strided)
+    void* stream = nullptr;          // the context's cudaStream_t: the NCCL all-reduce is enqueued here
+    void* comm = nullptr;            // ncclComm_t
+};
+
 class Reconstruction {
 public:
     explicit Reconstruction(int device);
+    // -d d0 d1 ...: one rank per device, driven by one host thread each; the volume accumulators are summed with
+    // ncclAllReduce over NVLink (replaces the reduce-to-device-0 + broadcast of cuda2.cu:2225-2239,2445-2460,2175-2180).
+    explicit Reconstruction(const std::vector<int>& devices);
     ~Reconstruction();
+    size_t NumberOfRanks() const { return devices_.size(); }
 
     double CreateTemplate(const Image& stack, double resolution);
     void SetMask(Image* mask, double sigma, double threshold = 0.5);
@@ -69,8 +83,13 @@ public:
 private:
     void ck(int rc, const char* what) const;
     void ensure_context();
-    int device_ = 0;
-    svr_context* c_ = nullptr;
+    void allreduce_accumulator(Rank& r);
+    template <class F> void each_rank(F&& f);
+    template <class T> std::vector<T> take(const Rank& r, const std::vector<T>& global, int stride = 1) const;
+    template <class T> void put(const Rank& r, const std::vector<T>& local, std::vector<T>& global, int stride = 1) const;
+    std::vector<int> devices_;
+    std::vector<Rank> ranks_;
+    svr_context* c_ = nullptr;       // rank 0's context (single-rank calls: profile read-outs, registration debug taps)
     Image reconstructed_, mask_;
     bool template_created_ = false, have_mask_ = false;
     std::vector<Image> slices_;                    // single-plane images

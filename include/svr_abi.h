@@ -46,6 +46,18 @@ int svr_abi_version(void);
 int svr_set_stream(svr_context *ctx, void *cuda_stream);
 /* Block until all queued work of the context is complete.  ref: cudaDeviceSynchronize calls. */
 int svr_synchronize(svr_context *ctx);
+/* The cudaStream_t the context launches on (its own, or the one given to svr_set_stream): a caller that issues collectives
+ * (ncclAllReduce on svr_device_buffer) enqueues them here, between the *_local and *_finish calls, with no host round trip. */
+int svr_get_stream(svr_context *ctx, void **cuda_stream);
+/* Asynchronous mode.  The reference's calls all return after a device synchronisation
+ * (cuda2.cu: cudaDeviceSynchronize / per-GPU cudaStreamSynchronize), and so do ours by default.  With on != 0 an entry point
+ * that returns no host data only ENQUEUES its work on the context's stream and returns; entry points that return host data
+ * (slice potentials, scale vector, statistics, volumes) still complete before they return.  Host input buffers must then stay
+ * valid until svr_synchronize (pageable memory is staged by the driver before the call returns; pinned memory is not). */
+int svr_set_async(svr_context *ctx, int on);
+/* Makes the context's device the calling thread's current device (and leaves it so): for a host thread that drives one rank
+ * and calls NCCL next to the library.  ref: cudaSetDevice(dev) at the top of every *OnX(dev), e.g. cuda2.cu:2385. */
+int svr_make_current(svr_context *ctx);
 /* Number of kernels this context has launched since creation (for bench.py's gpu_launches). */
 int64_t svr_launch_count(const svr_context *ctx);
 /* Kernel-variant selection for A/B measurements (tools/, bench.py --tune); results agree within float summation order.
@@ -258,6 +270,12 @@ int svr_host_small_slices(int S, const int *voxel_num, int *out_small, int *n_ou
  * slices_per_stack[n_stacks]; out_begin/out_end = this rank's [begin,end) in global slice order.
  * ref (what it replaces): floor(N/D)-sized ranges that drop the remainder, cuda2.cu:1413-1457. */
 int svr_host_partition(int n_stacks, const int *slices_per_stack, int nranks, int rank, int *out_begin, int *out_end);
+/* The balanced split bench.py and the C++ host use: rank r takes every nranks-th slice of EVERY stack (slice j of a stack with
+ * j % nranks == rank), so every rank sees the same mix of stack orientations and of positions along the stacks (the cost of the
+ * PSF kernels depends on both: whole stacks per rank measured 22 % imbalance at N = 2, contiguous ranges 60 % efficiency at
+ * N = 4).  out_indices receives the rank's slices as indices into the stack-major global order (capacity: sum of
+ * slices_per_stack), out_count their number.  ref: the contiguous split of cuda2.cu:1408-1457 (which also drops slices, Q6). */
+int svr_host_partition_strided(int n_stacks, const int *slices_per_stack, int nranks, int rank, int *out_indices, int *out_count);
 
 #ifdef __cplusplus
 }

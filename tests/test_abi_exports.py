@@ -82,3 +82,18 @@ def test_partition_covers_all_slices_once(built_lib, stacks, nranks):
         assert all(e > b for b, e in cuts)
     if stacks == [128] * 8:
         assert all(e - b == total // nranks for b, e in cuts)
+
+
+@pytest.mark.parametrize("stacks,nranks", [([128] * 8, 1), ([128] * 8, 8), ([98, 84, 84, 84], 4), ([10, 10, 10], 8), ([7], 3), ([], 2)])
+def test_strided_partition_is_a_balanced_cover(built_lib, stacks, nranks):
+    """svr_host_partition_strided: every slice exactly once, every rank the same share (+-1) of EVERY stack."""
+    total = sum(stacks)
+    parts = [R.host_partition_strided(stacks, nranks, r) for r in range(nranks)]
+    allidx = np.concatenate(parts) if parts else np.zeros(0, np.int32)
+    assert sorted(allidx.tolist()) == list(range(total))
+    bounds = np.cumsum([0] + stacks)
+    for st in range(len(stacks)):
+        per_rank = [int(np.count_nonzero((p >= bounds[st]) & (p < bounds[st + 1]))) for p in parts]
+        assert max(per_rank) - min(per_rank) <= 1
+    for p in parts:
+        assert np.all(np.diff(p) > 0)                 # ascending global order within a rank

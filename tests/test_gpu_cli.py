@@ -132,3 +132,49 @@ def test_cli_registration_pass_uses_device_resampling(cli, acquisition, tmp_path
     assert lines, r.stdout[-2000:]
     assert float(lines[0].rsplit(" ", 1)[1]) <= 2e-7, lines[0]      # one float ulp: the device holds the slices as float32
     assert (tmp_path / "image1_GPU.nii.gz").exists() and (tmp_path / "recon.nii.gz").exists()
+
+
+def test_cli_two_gpus_match_one_gpu(cli, acquisition, tmp_path):
+    """host/SVRreconstructionGPU -d 0 1: one rank (host thread) per device, slices sharded (svr_host_partition_strided), raw
+    ncclAllReduce of the volume accumulator from the C++ host -- against the same command on one device.  Two outer iterations
+    with the GPU slice-to-volume registration in between (every rank registers its own slices against its replica)."""
+    import gzip
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    a = acquisition
+    common = ["-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0", "--iterations", "2",
+                                    "--rec_iterations_last", "3", "--useGPUReg"]
+    vols = {}
+    for tag, dev in (("one", ["-d", "0"]), ("two", ["-d", "0", "1"])):
+        d = tmp_path / tag
+        d.mkdir()
+        r = run(cli, ["-o", "recon.nii.gz"] + common + dev, d)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        if tag == "two":
+            logs = r.stdout + "".join((d / n).read_text() for n in os.listdir(d) if n.startswith("log-"))
+            assert "NCCL: 2 ranks" in logs, logs[-2000:]
+        (d / "recon.nii").write_bytes(gzip.open(d / "recon.nii.gz").read())
+        vols[tag] = read_nifti(d / "recon.nii")[0]
+    one, two = vols["one"], vols["two"]
+    assert one.shape == two.shape and np.isfinite(two).all() and (two != 0).any()
+    scale = np.sqrt(np.mean(one[one != 0] ** 2))
+    d = np.abs(two - one) / scale
+    # the ranks' partial sums are added in a different order than one GPU's atomics; the registration in between amplifies
+    # that (greedy line searches), so this is a loose bound on a 2-iteration run, and a tight one on the first image
+    i1 = read_nifti_gz(tmp_path / "one" / "image0_GPU.nii.gz"); i2 = read_nifti_gz(tmp_path / "two" / "image0_GPU.nii.gz")
+    d0 = np.abs(i2 - i1) / np.sqrt(np.mean(i1[i1 != 0] ** 2))
+    assert np.sqrt(np.mean(d0 ** 2)) <= 1e-5 and d0.max() <= 1e-3, (np.sqrt(np.mean(d0 ** 2)), d0.max())
+    assert np.sqrt(np.mean(d ** 2)) <= 5e-2, (np.sqrt(np.mean(d ** 2)), d.max())
+
+
+def read_nifti_gz(path):
+    import gzip
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".nii", delete=False) as f:
+        f.write(gzip.open(path).read())
+        name = f.name
+    try:
+        return read_nifti(name)[0]
+    finally:
+        os.unlink(name)
