@@ -236,7 +236,82 @@ def cpu_step(ds):
     return total, volume_side
 
 
+def attrs18(a):
+    """ImageAttributes -> the 18 doubles irtkImageAttributes is built from (oracle/ref_irtk.py)."""
+    return np.concatenate([[a.x, a.y, a.z, a.dx, a.dy, a.dz], np.asarray(a.origin, float), np.asarray(a.xaxis, float),
+                           np.asarray(a.yaxis, float), np.asarray(a.zaxis, float)])
+
+
+def reference_cpu_step(ds, threads):
+    """One outer iteration of the REFERENCE'S OWN CPU (--useCPU) path: class irtkReconstruction of irtkReconstructionGPU.cc and the
+    vendored IRTK, compiled unmodified into oracle/_ref/libref_irtk.so (TBB stand-in on std::thread).  The call order is the
+    useCPU branch of reconstruction.cc:800-1138: InitializeEM, InitializeEMValues, CoeffInit, GaussianReconstruction,
+    SimulateSlices, InitializeRobustStatistics, EStep, 4 x (Scale, Superresolution, SimulateSlices, MStep, EStep), MaskVolume."""
+    from oracle import ref_irtk as ri
+    ri.set_threads(threads)
+    r = ri.Reconstruction()
+    vol = attrs18(ds.vol_attr) if hasattr(ds, "vol_attr") else None
+    if vol is None:                                          # C2 fixture: the volume grid from its matrices
+        from fetalreconstruction_b200.geometry import ImageAttributes
+        vz, vy, vx = ds.mask.shape
+        i2w = np.asarray(ds.recon_i2w, np.float64).reshape(4, 4)
+        d = float(ds.cfg.vol_voxel)
+        ax = [i2w[:3, c] / d for c in range(3)]
+        centre = i2w @ np.array([(vx - 1) / 2.0, (vy - 1) / 2.0, (vz - 1) / 2.0, 1.0])
+        vol = attrs18(ImageAttributes(vx, vy, vz, d, d, d, centre[:3], ax[0], ax[1], ax[2]))
+    r.set_reconstructed(ri.Image.new(vol))
+    r.set_mask(ri.Image.new(vol, ds.mask.astype(np.float64)), 0.0)
+    imgs = []
+    for k in range(ds.S):
+        a = ds.slice_attrs[k]
+        sx, sy = a.x, a.y
+        imgs.append(ri.Image.new(attrs18(a), ds.slices[k, :sy, :sx].astype(np.float64)))
+    dofs = np.stack([ri.rigid_from_matrix(np.asarray(t, np.float64).reshape(4, 4)) for t in ds.trans])
+    r.set_slices(imgs, dofs, np.asarray(ds.stack_index, np.int32), np.asarray(ds.dims[:, 2], np.float64))
+    r.cpu_step("InitializeEM")
+    times = {}
+
+    def step(name, it=0):
+        t = time.perf_counter()
+        r.cpu_step(name, it)
+        times[name] = times.get(name, 0.0) + time.perf_counter() - t
+    t0 = time.perf_counter()
+    r.call("set_smoothing_parameters", 150.0, 0.08)         # iteration 0 of the default schedule (reconstruction.cc:900-911)
+    r.call("speedup", 1)
+    step("InitializeEMValues"); step("CoeffInit"); step("GaussianReconstruction"); step("SimulateSlices")
+    step("InitializeRobustStatistics"); step("EStep")
+    for i in range(4):
+        step("Scale"); step("Superresolution", i + 1); step("SimulateSlices"); step("MStep", i + 1); step("EStep")
+    step("MaskVolume")
+    total = time.perf_counter() - t0
+    vol_out = r.reconstructed().data
+    return total, times, bool(np.isfinite(vol_out).all() and (vol_out > 0).any())
+
+
 def run_cpu_baseline(args, cfg, S_full, steps=1, warmup=0):
+    """The CPU arm: the reference's own CPU path when oracle/_ref/libref_irtk.so is there (kind "reference"), else our restatement
+    of it (kind "port", oracle/cpu_path.c)."""
+    from oracle import ref_irtk as ri
+    if ri.available() and not os.environ.get("SVR_BENCH_CPU_PORT"):
+        threads = host_threads()
+        ds, sample = cpu_sample_dataset(args, cfg)
+        for _ in range(warmup):
+            reference_cpu_step(ds, threads)
+        runs = [reference_cpu_step(ds, threads) for _ in range(max(steps, 1))]
+        t = float(np.mean([r[0] for r in runs]))
+        times = runs[-1][1]
+        # volume-side work that does not grow with the slices: the regulariser inside Superresolution cannot be separated by timing
+        # the calls, so the extrapolation scales EVERYTHING with the slices (conservative for the CPU: it over-counts its time)
+        t_full = t * S_full / ds.S
+        sampled = ds.S != S_full
+        return {"value": S_full * PROJ_PER_SLICE_STEP / t_full, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": f"{sample}; one outer iteration (10 slice-projections per slice) of the reference's OWN CPU (--useCPU) path -- class "
+                          "irtkReconstruction (irtkReconstructionGPU.cc: CoeffInit, GaussianReconstruction, SimulateSlices, EStep, Scale, "
+                          "Superresolution, MStep) + the vendored IRTK, compiled unmodified into oracle/_ref/libref_irtk.so; its TBB "
+                          f"parallel_for / parallel_reduce run on a std::thread stand-in with {threads} threads -- took {t:.1f} s"
+                          + (f"; `value` is the full-workload figure, time x {S_full}/{ds.S} = {t_full:.1f} s per step" if sampled else ""),
+                "seconds_per_step_sample": t, "seconds_per_step_full_workload": t_full, "finite": runs[-1][2],
+                "seconds_by_call": {k: round(v, 2) for k, v in times.items()}}, t_full
     from oracle import oracle as orc
     # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU arm sets its thread count itself
     orc.set_num_threads(host_threads())

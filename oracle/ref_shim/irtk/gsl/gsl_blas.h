@@ -1,0 +1,1 @@
+#include "gsl_shim.h"

@@ -1,0 +1,1 @@
+#include "tbb_shim.h"
