@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libsvr_b200.so")
-SOURCES = ["svr_abi.cu", "svr_psf.cu", "svr_window.cu", "svr_em.cu", "svr_reg.cu", "pvr_abi.cu"]
+SOURCES = ["svr_abi.cu", "svr_psf.cu", "svr_window.cu", "svr_em.cu", "svr_reg.cu", "svr_rreg.cu", "pvr_abi.cu"]
 HEADERS = ["svr_common.cuh", "svr_context.h", "svr_psf_pixel.cuh", os.path.join("..", "..", "include", "svr_abi.h"),
            os.path.join("..", "..", "include", "pvr_abi.h")]
 

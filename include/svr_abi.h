@@ -277,6 +277,31 @@ int svr_host_partition(int n_stacks, const int *slices_per_stack, int nranks, in
  * slices_per_stack), out_count their number.  ref: the contiguous split of cuda2.cu:1408-1457 (which also drops slices, Q6). */
 int svr_host_partition_strided(int n_stacks, const int *slices_per_stack, int nranks, int rank, int *out_indices, int *out_count);
 
+/* ---- IRTK-style rigid registration on the device (csrc/svr_rreg.cu) ---------------------------------------------------
+ * The engine behind the reference's DEFAULT registrations, which all run irtkImageRigidRegistrationWithPadding on the CPU:
+ *   kind 0  stack-to-template      ref: irtkReconstruction::StackRegistrations, irtkReconstructionGPU.cc:849-1001
+ *                                       (GuessParameterThickSlices, SetTargetPadding(0))
+ *   kind 1  slice / patch to volume ref: ParallelSliceToVolumeRegistration, irtkReconstructionGPU.cc:1992-2059, and
+ *                                       ParallelPatchToVolumeRegistration, patchBased2D3DRegistration.cpp:88-168
+ *                                       (GuessParameterSliceToVolume(false), SetTargetPadding(-1))
+ * Images are the reference's irtkGreyImage: short voxels (x fastest) + the 18 numbers of irtkImageAttributes
+ * {x, y, z, dx, dy, dz, origin[3], xaxis[3], yaxis[3], zaxis[3]}.  voxels[n_images] / attrs18[n_images][18] list the images;
+ * item i registers target images[target_of_item[i]] to source images[source_of_item[i]], starting from and returning
+ * dofs[6 i ..] = {tx, ty, tz (mm), rx, ry, rz (degrees)} (irtkRigidTransformation).  similarity (may be NULL) receives the final
+ * cross-correlation per item, evaluations (may be NULL) the number of similarity evaluations.
+ * level_only >= 0 (test tap): no optimisation; that resolution level is prepared, similarity[i] = the metric at dofs, and item 0's
+ * prepared target / source images are copied out (buffers sized like the originals; NULL to skip). */
+int svr_rreg_register(svr_context *ctx, int n_items, int n_images, const short *const *voxels, const double *attrs18,
+                      const int *target_of_item, const int *source_of_item, int kind, double *dofs, double *similarity,
+                      int64_t *evaluations, int level_only, short *prepared_target, double *prepared_target_attr18,
+                      short *prepared_source, double *prepared_source_attr18);
+/* The reference's padded image filters on the device, on their own:
+ * ref: irtkGaussianBlurringWithPadding<irtkGreyPixel>::Run (image++/src/irtkGaussianBlurringWithPadding.cc:36-117) */
+int svr_rreg_blur_with_padding(svr_context *ctx, const short *voxels, const double attr18[18], double sigma, int padding, short *out);
+/* ref: irtkResamplingWithPadding<irtkGreyPixel>::Run (image++/src/irtkResamplingWithPadding.cc:36-183, irtkResampling.cc:74-131) */
+int svr_rreg_resample_with_padding(svr_context *ctx, const short *voxels, const double attr18[18], double dx, double dy, double dz,
+                                   int padding, short *out, size_t out_capacity, double out_attr18[18]);
+
 #ifdef __cplusplus
 }
 #endif
