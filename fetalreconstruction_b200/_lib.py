@@ -111,7 +111,7 @@ _SIGNATURES = {
     "pvr_rs_mstep": (ip, [vp, ip, fp, F, F, F]),
     "pvr_rs_scale": (ip, [vp, vp]),
     "pvr_debug_get": (ip, [vp, ip, vp]),
-    "svr_rreg_register": (ip, [vp, ip, ip, vp, vp, vp, vp, ip, vp, vp, vp, ip, vp, vp, vp, vp]),
+    "svr_rreg_register": (ip, [vp, ip, ip, vp, vp, vp, vp, ip, vp, vp, vp, ip, C.c_size_t, vp, vp, vp, vp]),
     "svr_rreg_blur_with_padding": (ip, [vp, vp, vp, dp, ip, vp]),
     "svr_rreg_resample_with_padding": (ip, [vp, vp, vp, dp, dp, dp, ip, vp, C.c_size_t, vp]),
     "svr_host_slice_em": (ip, [ip, vp, vp, vp, vp, ip, vp, ip, dp, vp]),

@@ -527,9 +527,9 @@ int svr_rreg_resample_with_padding(svr_context* c, const short* voxels, const do
 // item i registers images[target_of_item[i]] (target) to images[source_of_item[i]] (source) starting from dofs[6 i .. 6 i + 5]
 // (tx, ty, tz in mm, rx, ry, rz in degrees), which receive the result.  kind 0 / 1: see the header.  level_only >= 0: prepare only
 // that level and return the similarity of the given parameters in similarity[i] without optimising (test tap);
-// prepared_target / prepared_source (may be NULL): receive item 0's prepared images of that level (capacity = the original sizes).
+// prepared_target / prepared_source (may be NULL): receive item 0's prepared images of that level (prepared_capacity voxels each).
 int svr_rreg_register(svr_context* c, int n_items, int n_images, const short* const* voxels, const double* attrs18, const int* target_of_item,
-                      const int* source_of_item, int kind, double* dofs, double* similarity, int64_t* evaluations, int level_only,
+                      const int* source_of_item, int kind, double* dofs, double* similarity, int64_t* evaluations, int level_only, size_t prepared_capacity,
                       short* prepared_target, double* prepared_target_attr18, short* prepared_source, double* prepared_source_attr18)
 {
     SVR_ENTRY(c);
@@ -589,6 +589,7 @@ int svr_rreg_register(svr_context* c, int n_items, int n_images, const short* co
             auto dump = [&](int id, short* out, double* a18) -> int {
                 if (!out) return 0;
                 const DevImg& d = prepared[id];
+                if (d.n() > prepared_capacity) { c->err = "svr_rreg_register: prepared-image buffer too small"; return 2; }
                 SVR_CUDA(c, cudaMemcpyAsync(out, d.d, d.n() * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
                 SVR_CUDA(c, cudaStreamSynchronize(c->stream));
                 if (a18) attr_to18(d.a, a18);

@@ -45,12 +45,14 @@ def register(backend, images, attrs, target_of_item, source_of_item, kind, dofs,
     sim = np.zeros(max(n_items, 1), np.float64)
     ev = C.c_int64(0)
     pt = ps = pta = psa = None
+    cap = 0
     if level_only >= 0 and want_prepared:
-        pt = np.zeros(imgs[ti[0]].size, np.int16); ps = np.zeros(imgs[si[0]].size, np.int16)
+        cap = 4 * max(imgs[ti[0]].size, imgs[si[0]].size) + 1024      # resampling can enlarge an image (finer target resolution)
+        pt = np.zeros(cap, np.int16); ps = np.zeros(cap, np.int16)
         pta = np.zeros(18); psa = np.zeros(18)
     p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     rc = lib.svr_rreg_register(_ctx(backend), n_items, n_images, ptrs, p(at), p(ti), p(si), int(kind), p(d), p(sim), C.byref(ev), int(level_only),
-                               p(pt), p(pta), p(ps), p(psa))
+                               cap, p(pt), p(pta), p(ps), p(psa))
     if rc != 0:
         raise SVRError(lib.svr_last_error(_ctx(backend)).decode())
     if level_only >= 0:

@@ -290,10 +290,10 @@ int svr_host_partition_strided(int n_stacks, const int *slices_per_stack, int nr
  * dofs[6 i ..] = {tx, ty, tz (mm), rx, ry, rz (degrees)} (irtkRigidTransformation).  similarity (may be NULL) receives the final
  * cross-correlation per item, evaluations (may be NULL) the number of similarity evaluations.
  * level_only >= 0 (test tap): no optimisation; that resolution level is prepared, similarity[i] = the metric at dofs, and item 0's
- * prepared target / source images are copied out (buffers sized like the originals; NULL to skip). */
+ * prepared target / source images are copied out (buffers of prepared_capacity voxels each; NULL to skip). */
 int svr_rreg_register(svr_context *ctx, int n_items, int n_images, const short *const *voxels, const double *attrs18,
                       const int *target_of_item, const int *source_of_item, int kind, double *dofs, double *similarity,
-                      int64_t *evaluations, int level_only, short *prepared_target, double *prepared_target_attr18,
+                      int64_t *evaluations, int level_only, size_t prepared_capacity, short *prepared_target, double *prepared_target_attr18,
                       short *prepared_source, double *prepared_source_attr18);
 /* The reference's padded image filters on the device, on their own:
  * ref: irtkGaussianBlurringWithPadding<irtkGreyPixel>::Run (image++/src/irtkGaussianBlurringWithPadding.cc:36-117) */
