@@ -2,9 +2,10 @@
 // over the B200 library.  Same option names, defaults, call order, log files and output file names as the reference's
 // GPU path.  What differs (printed at start-up):
 //   * there is no CPU path: --useCPU is refused (no CPU fallback by design);
-//   * slice-to-volume registration always runs on the GPU (the reference's --useGPUReg behaviour); the IRTK CPU
-//     registration behind the reference's default --useCPUReg and the 3D stack-to-stack registration
-//     (StackRegistrations) are not restated: stacks enter with the -t transformations;
+//   * every registration runs on the GPU: the reference's default IRTK registrations (--useCPUReg: StackRegistrations and the
+//     per-slice irtkImageRigidRegistrationWithPadding, on the CPU through TBB there) on the device engine svr_rreg_register
+//     (same optimiser path, bit for bit), --useGPUReg the NCC registration of Reconstruction::registerSlicesToVolume;
+//     --noStackRegistration (not a reference option) skips the volumetric stack registration for pre-aligned input;
 //   * --patchBased / --superpixelBased belong to PVRreconstructionGPU and are refused here.
 // The option parser restates the boost::program_options behaviour the reference relies on: multitoken options take
 // every following token up to the next option; po::value<bool> options take a value; bool_switch options take none.
@@ -74,7 +75,7 @@ struct Options {
            low_intensity_cutoff = 0.01;
     bool global_bias_correction = false, intensity_matching = true, debug = false, debug_gpu = false, no_log = false;
     unsigned rec_iterations_first = 4, rec_iterations_last = 13, num_stacks_tuner = 0, T1PackageSize = 0, patchSize = 64, patchStride = 32;
-    bool useCPU = false, useCPUReg = true, useGPUReg = false, useAutoTemplate = false, disableBiasCorr = true, patchBased = false,
+    bool useCPU = false, useCPUReg = true, useGPUReg = false, useAutoTemplate = false, disableBiasCorr = true, patchBased = false, noStackRegistration = false,
          superpixelBased = false, useNMI = false, saveSliceTransformations = false;
     float superpixel = 0;
 };
@@ -176,6 +177,7 @@ bool parse(int argc, char** argv, Options& o, bool& help)
         else if (a == "--useCPU") o.useCPU = true;
         else if (a == "--useCPUReg") o.useCPUReg = true;
         else if (a == "--useGPUReg") o.useGPUReg = true;
+        else if (a == "--noStackRegistration") o.noStackRegistration = true;
         else if (a == "--useAutoTemplate") o.useAutoTemplate = true;
         else if (a == "--patchSize") { if (!one(a, v)) return false; o.patchSize = (unsigned)atoi(v.c_str()); }
         else if (a == "--patchStride") { if (!one(a, v)) return false; o.patchStride = (unsigned)atoi(v.c_str()); }
@@ -213,8 +215,7 @@ int main(int argc, char** argv)
         std::cerr << "FATAL ERROR: --packages / --T1PackageSize / --sfolder / --manualMask / --useAutoTemplate are not supported by this build." << std::endl;
         return EXIT_FAILURE;
     }
-    if (!o.useGPUReg) std::cout << "NOTE: slice-to-volume registration runs on the GPU (--useGPUReg behaviour); the IRTK CPU registration is not part of this build." << std::endl;
-    std::cout << "NOTE: stack-to-stack (3D) registration is not part of this build; stacks are used with the -t transformations (identity if none)." << std::endl;
+    if (!o.useGPUReg) std::cout << "Slice-to-volume and stack registration: the reference's default IRTK rigid registration (cross-correlation, 3 levels), on the GPU." << std::endl;
 
     std::cout << "Reconstructed volume name ... " << o.output << std::endl;
     size_t nStacks = o.input.size();
@@ -323,7 +324,11 @@ int main(int argc, char** argv)
     std::cout << std::setprecision(3);
     std::cerr << std::setprecision(3);
 
-    // (StackRegistrations would run here, reconstruction.cc:660-675: not part of this build)
+    // volumetric registration of the stacks to the template (reconstruction.cc:651-662), on the device engine
+    const bool stack_registration = o.T1PackageSize == 0 && o.sfolder.empty() && !o.noStackRegistration;
+    if (!o.no_log) { std::cerr.rdbuf(file_e.rdbuf()); std::cout.rdbuf(file.rdbuf()); }
+    if (stack_registration) reconstruction.StackRegistrations(stacks, stack_transformations, templateNumber);
+    if (!o.no_log) { std::cout.rdbuf(strm_buffer); std::cerr.rdbuf(strm_buffer_e); }
 
     for (size_t i = 0; i < nStacks; ++i) {         // crop the other stacks with the transformed mask (reconstruction.cc:686-707)
         if ((int)i == templateNumber) continue;
@@ -332,6 +337,12 @@ int main(int argc, char** argv)
         reconstruction.CropImage(stacks[i], m);
         if (o.debug) { snprintf(buffer, sizeof(buffer), "cropped%zu.nii.gz", i); write_or_die(buffer, stacks[i]); }
     }
+
+    // "Repeat volumetric registrations with cropped stacks" (reconstruction.cc:702-714)
+    if (!o.no_log) { std::cerr.rdbuf(file_e.rdbuf()); std::cout.rdbuf(file.rdbuf()); }
+    if (stack_registration) reconstruction.StackRegistrations(stacks, stack_transformations, templateNumber);
+    if (!o.no_log) { std::cout.rdbuf(strm_buffer); std::cerr.rdbuf(strm_buffer_e); }
+    stats.sample("StackRegistrations");
 
     reconstruction.MatchStackIntensitiesWithMasking(stacks, stack_transformations, o.average, !o.intensity_matching);
     reconstruction.CreateSlicesAndTransformations(stacks, stack_transformations, thickness);
@@ -349,7 +360,7 @@ int main(int argc, char** argv)
     const auto tick = std::chrono::steady_clock::now();
 
     reconstruction.SyncGPU();
-    reconstruction.PrepareRegistrationSlices();
+    if (o.useGPUReg) reconstruction.PrepareRegistrationSlices();
     stats.sample("SyncGPU");
     reconstruction.InitializeEMGPU();
     stats.sample("InitializeEM");
@@ -364,9 +375,14 @@ int main(int argc, char** argv)
             if (!o.no_log) { std::cerr.rdbuf(file_e.rdbuf()); std::cout.rdbuf(file.rdbuf()); }
             std::cout << "Iteration " << iter << ": " << std::endl;
             std::cout << "Slice To Volume Registration " << ": " << std::endl;
-            printf("Slice To Volume Registration GPU\n");
-            std::cout << "Slice To Volume Registration GPU" << ": " << std::endl;
-            reconstruction.SliceToVolumeRegistrationGPU();
+            if (o.useGPUReg) {                       // reconstruction.cc:868-879
+                printf("Slice To Volume Registration GPU\n");
+                std::cout << "Slice To Volume Registration GPU" << ": " << std::endl;
+                reconstruction.SliceToVolumeRegistrationGPU();
+            } else {
+                std::cout << "Slice To Volume Registration (IRTK rigid registration, device engine)" << ": " << std::endl;
+                reconstruction.SliceToVolumeRegistration();
+            }
             stats.sample("Registration");
             std::cout << std::endl;
             if (!o.no_log) std::cerr.rdbuf(strm_buffer_e);

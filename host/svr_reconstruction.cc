@@ -702,6 +702,119 @@ void Reconstruction::SliceToVolumeRegistrationGPU()
     }
 }
 
+// ---- the reference's default (IRTK) registrations on the device engine -------------------------------------------------------
+static void attr18(const ImageAttr& a, double* o)
+{
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.dx; o[4] = a.dy; o[5] = a.dz;
+    for (int i = 0; i < 3; ++i) { o[6 + i] = a.origin[i]; o[9 + i] = a.xaxis[i]; o[12 + i] = a.yaxis[i]; o[15 + i] = a.zaxis[i]; }
+}
+// irtkGreyImage = irtkRealImage: static_cast<short> per voxel (image++/src/irtkGenericImage.cc:699-713)
+static std::vector<short> to_grey(const Image& im)
+{
+    std::vector<short> g(im.n());
+    for (size_t i = 0; i < g.size(); ++i) g[i] = static_cast<short>(im.v[i]);
+    return g;
+}
+// ResetOrigin (irtkReconstructionGPU.cc:823-834): the image origin moves into a translation
+static Mat4 reset_origin(ImageAttr& a)
+{
+    Mat4 mo = Mat4::identity();
+    for (int q = 0; q < 3; ++q) { mo.m[q][3] = a.origin[q]; a.origin[q] = 0; }
+    return mo;
+}
+
+// StackRegistrations, irtkReconstructionGPU.cc:940-1001 + ParallelStackRegistrations :849-938
+void Reconstruction::StackRegistrations(std::vector<Image>& stacks, std::vector<Rigid>& stack_transformations, int templateNumber)
+{
+    ensure_context();
+    if (stacks.size() < 2) return;
+    InvertStackTransformations(stack_transformations);
+    Image target = stacks[templateNumber];
+    std::vector<short> tgrey = to_grey(target);
+    if (have_mask_) {                                  // the target is masked before registration (:957-984)
+        const Mat4 t_i2w = target.a.image_to_world(), m_w2i = mask_.a.world_to_image();
+        for (int k = 0; k < target.a.z; ++k) for (int j = 0; j < target.a.y; ++j) for (int i = 0; i < target.a.x; ++i) {
+            double x = i, y = j, z = k;
+            t_i2w.apply(x, y, z);
+            m_w2i.apply(x, y, z);
+            const double rx = std::round(x), ry = std::round(y), rz = std::round(z);
+            bool keep = false;
+            if (rx >= 0 && rx < mask_.a.x && ry >= 0 && ry < mask_.a.y && rz >= 0 && rz < mask_.a.z) keep = mask_.at((int)rx, (int)ry, (int)rz) != 0;
+            if (!keep) tgrey[((size_t)k * target.a.y + j) * target.a.x + i] = 0;
+        }
+    }
+    ImageAttr ta = target.a;
+    const Mat4 mo = reset_origin(ta);
+    std::vector<std::vector<short>> grey;
+    std::vector<const short*> vox;
+    std::vector<double> attrs;
+    std::vector<int> tgt, src, which;
+    std::vector<double> dofs;
+    grey.push_back(tgrey);
+    attrs.resize(18); attr18(ta, attrs.data());
+    for (size_t i = 0; i < stacks.size(); ++i) {
+        if ((int)i == templateNumber) continue;        // "do not perform registration for template"
+        grey.push_back(to_grey(stacks[i]));
+        attrs.resize(attrs.size() + 18); attr18(stacks[i].a, attrs.data() + attrs.size() - 18);
+        stack_transformations[i] = Rigid::from_matrix(stack_transformations[i].matrix() * mo);     // include the offset (:889-892)
+        tgt.push_back(0); src.push_back((int)grey.size() - 1); which.push_back((int)i);
+        for (int q = 0; q < 6; ++q) dofs.push_back(stack_transformations[i].p[q]);
+    }
+    for (auto& g : grey) vox.push_back(g.data());
+    int64_t evals = 0;
+    ck(svr_rreg_register(c_, (int)tgt.size(), (int)vox.size(), vox.data(), attrs.data(), tgt.data(), src.data(), 0, dofs.data(), nullptr, &evals, -1, 0,
+                         nullptr, nullptr, nullptr, nullptr), "StackRegistrations");
+    const Mat4 moi = mo.inverse();
+    for (size_t a = 0; a < which.size(); ++a) {
+        Rigid t; for (int q = 0; q < 6; ++q) t.p[q] = dofs[6 * a + q];
+        stack_transformations[which[a]] = Rigid::from_matrix(t.matrix() * moi);
+        std::cout << "stack " << which[a] << " registered to the template: " << t.p[0] << " " << t.p[1] << " " << t.p[2] << " " << t.p[3] << " " << t.p[4] << " "
+                  << t.p[5] << std::endl;
+    }
+    std::cout << "StackRegistrations: " << evals << " similarity evaluations on the device" << std::endl;
+    InvertStackTransformations(stack_transformations);
+}
+
+// SliceToVolumeRegistration (the reference's default, CPU / IRTK), irtkReconstructionGPU.cc:1992-2059, on the device engine:
+// every slice resampled to the volume's voxel size with padding (host, double, as there), cast to short, origin reset; the
+// volume (SyncCPU copy) cast to short is the shared source.
+void Reconstruction::SliceToVolumeRegistration()
+{
+    const double d = reconstructed_.a.dx;
+    const std::vector<short> source = to_grey(reconstructed_);
+    each_rank([&](Rank& r) {
+        std::vector<std::vector<short>> grey;
+        std::vector<const short*> vox;
+        std::vector<double> attrs(18), dofs;
+        std::vector<int> tgt, src, which;
+        std::vector<Mat4> mos;
+        attr18(reconstructed_.a, attrs.data());
+        for (int gi : r.idx) {
+            Image t = resample_slice_with_padding(slices_[gi], d, -1);
+            std::vector<short> g = to_grey(t);
+            short smax = -32768;
+            for (short v : g) smax = std::max(smax, v);
+            if (!(smax > -1)) continue;                  // "if (smax > -1)": empty slices keep their transformation
+            ImageAttr a = t.a;
+            const Mat4 mo = reset_origin(a);
+            const Rigid start = Rigid::from_matrix(transformations_[gi].matrix() * mo);
+            grey.push_back(std::move(g));
+            attrs.resize(attrs.size() + 18); attr18(a, attrs.data() + attrs.size() - 18);
+            tgt.push_back((int)grey.size()); src.push_back(0); which.push_back(gi); mos.push_back(mo);
+            for (int q = 0; q < 6; ++q) dofs.push_back(start.p[q]);
+        }
+        if (which.empty()) return;
+        vox.push_back(source.data());
+        for (auto& g : grey) vox.push_back(g.data());
+        RCK(r, svr_rreg_register(r.c, (int)which.size(), (int)vox.size(), vox.data(), attrs.data(), tgt.data(), src.data(), 1, dofs.data(), nullptr, nullptr,
+                                 -1, 0, nullptr, nullptr, nullptr, nullptr), "SliceToVolumeRegistration");
+        for (size_t a = 0; a < which.size(); ++a) {
+            Rigid t; for (int q = 0; q < 6; ++q) t.p[q] = dofs[6 * a + q];
+            transformations_[which[a]] = Rigid::from_matrix(t.matrix() * mos[a].inverse());          // undo the offset
+        }
+    });
+}
+
 // ---- EvaluateGPU, irtkReconstructionGPU.cc:4503-4538 ----------------------------------------------------------------
 void Reconstruction::EvaluateGPU(int iter, std::ostream& os)
 {

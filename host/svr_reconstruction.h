@@ -70,6 +70,11 @@ public:
     void SyncCPU();
     void PrepareRegistrationSlices();
     void SliceToVolumeRegistrationGPU();
+    // The reference's DEFAULT registrations (IRTK's irtkImageRigidRegistrationWithPadding on the CPU through TBB), on the device
+    // engine svr_rreg_register: StackRegistrations irtkReconstructionGPU.cc:940-1001, SliceToVolumeRegistration :1992-2059, :2291-2303
+    void StackRegistrations(std::vector<Image>& stacks, std::vector<Rigid>& stack_transformations, int templateNumber);
+    void SliceToVolumeRegistration();
+    void InvertStackTransformations(std::vector<Rigid>& t) const { for (Rigid& r : t) r.invert(); }
     void EvaluateGPU(int iter, std::ostream& os);
 
     const Image& GetReconstructedGPU() const { return reconstructed_; }

@@ -43,6 +43,17 @@ static irtkRigidTransformation rigid_from(const double* d)
 }
 static void rigid_to(const irtkRigidTransformation& t, double* d) { for (int i = 0; i < 6; ++i) d[i] = t.Get(i); }
 
+// The GPU member `Reconstruction* reconstructionGPU` is created by a stubbed (do-nothing) constructor: give it the all-zero state
+// of default-constructed members, so that the inline helpers the host class calls on it (updateStackSizes: a vector assignment)
+// operate on valid empty containers.
+struct RecoAccess : public irtkReconstruction {
+    RecoAccess(std::vector<int> dev, bool useCPUReg) : irtkReconstruction(dev, useCPUReg)
+    {
+        memset((void*)reconstructionGPU, 0, sizeof(Reconstruction));
+        reconstructionGPU->_useCPUReg = useCPUReg;
+    }
+};
+
 struct Ctx {
     irtkReconstruction* r;
     std::vector<irtkRealImage> stacks;
@@ -169,7 +180,7 @@ void* rirtk_create(void)
 {
     Ctx* c = new Ctx();
     std::vector<int> dev(1, 0);
-    c->r = new irtkReconstruction(dev, true);
+    c->r = new RecoAccess(dev, true);
     return c;
 }
 #define R(c) (((Ctx*)(c))->r)

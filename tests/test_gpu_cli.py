@@ -20,7 +20,7 @@ def test_cli_end_to_end_matches_python_host(cli, acquisition, tmp_path):
     from fetalreconstruction_b200.pipeline import SVRPipeline, SVRParams, upload_dataset
     from fetalreconstruction_b200.reconstruction import Reconstruction
     a = acquisition
-    common = ["-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0", "--iterations", "1",
+    common = ["-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0", "--noStackRegistration", "--iterations", "1",
                                     "--rec_iterations_last", "3"]
     dump = tmp_path / "dump"
     dump.mkdir()
@@ -125,7 +125,7 @@ def test_cli_registration_pass_uses_device_resampling(cli, acquisition, tmp_path
     """Two outer iterations: the second starts with SliceToVolumeRegistrationGPU, whose input slices are resampled on the
     device (svr_reg_resample_slices); --debug makes the host evaluate the same rules and print the largest difference."""
     a = acquisition
-    r = run(cli, ["-o", "recon.nii.gz", "-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0",
+    r = run(cli, ["-o", "recon.nii.gz", "-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0", "--noStackRegistration",
                   "--iterations", "2", "--rec_iterations_first", "2", "--rec_iterations_last", "2", "--debug", "1", "--no_log", "1"], tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = [l for l in r.stdout.splitlines() if "device vs host resampling" in l]
@@ -143,7 +143,7 @@ def test_cli_two_gpus_match_one_gpu(cli, acquisition, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     a = acquisition
-    common = ["-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0", "--iterations", "2",
+    common = ["-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0", "--noStackRegistration", "--iterations", "2",
                                     "--rec_iterations_last", "3", "--useGPUReg"]
     vols = {}
     for tag, dev in (("one", ["-d", "0"]), ("two", ["-d", "0", "1"])):
@@ -178,3 +178,82 @@ def read_nifti_gz(path):
         return read_nifti(name)[0]
     finally:
         os.unlink(name)
+
+
+def test_cli_setup_and_stack_registration_match_the_reference_irtk(cli, tmp_path):
+    """n1 + n3 pinned against the reference's own host code (oracle/_ref/libref_irtk.so: class irtkReconstruction + the vendored
+    IRTK, compiled unmodified).  Three stacks of ONE phantom, the second and third written with a wrong NIfTI position (a rigid
+    offset); both sides run the reference's set-up order (reconstruction.cc:566-756): crop the template with the mask,
+    CreateTemplate, SetMask, StackRegistrations, crop the other stacks with the transformed mask, StackRegistrations again,
+    MatchStackIntensitiesWithMasking, CreateSlicesAndTransformations, MaskSlices -- ours through the C++ CLI (NIfTI reader, host
+    set-up pipeline, device registration engine), theirs through IRTK's own reader and methods."""
+    from oracle import ref_irtk as ri
+    if not ri.available():
+        pytest.skip("oracle/_ref/libref_irtk.so not built")
+    from fetalreconstruction_b200.geometry import rigid_matrix
+    from fetalreconstruction_b200.phantom import make_dataset, small_config
+    from test_host_cli import write_nifti
+    cfg = small_config(seed=11, vol=56, n_stacks=3, slices=22, size=52, inplane=1.1, spacing=2.0)
+    cfg.motion_mm = cfg.motion_deg = 0.0
+    cfg.noise = 3.0
+    cfg.corrupt_fraction = 0.0
+    cfg.mask_semi_axis = 0.34
+    ds = make_dataset(cfg)
+    n = cfg.slices_per_stack
+    offsets = [np.zeros(6), np.array([2.0, -1.5, 1.0, 2.0, -1.0, 3.0]), np.array([-1.0, 2.5, -2.0, -3.0, 2.0, 1.0])]
+    names = []
+    for s, attr in enumerate(ds.stack_attrs):
+        vol = np.where(ds.slices[s * n:(s + 1) * n] < 0, 0.0, ds.slices[s * n:(s + 1) * n]).astype(np.float32)
+        # the phantom outside the mask is unknown to ds.slices (-1): give the stacks a smooth background so that cropping matters
+        aff = rigid_matrix(*offsets[s]) @ attr.image_to_world()
+        p = str(tmp_path / f"stack_{s}.nii")
+        write_nifti(p, vol, aff, (attr.dx, attr.dy, attr.dz))
+        names.append(p)
+    mp = str(tmp_path / "mask.nii")
+    write_nifti(mp, ds.mask.astype(np.float32), ds.vol_attr.image_to_world(), (cfg.vol_voxel,) * 3)
+
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    r = run(cli, ["-o", "recon.nii.gz", "-i"] + names + ["-m", mp, "--resolution", "1.0", "--smooth_mask", "0", "--dump_setup", str(dump)], tmp_path)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    idx = dict(line.split() for line in open(dump / "index.txt"))
+    S, Nx, Ny = int(idx["S"]), int(idx["Nx"]), int(idx["Ny"])
+    slices = np.fromfile(dump / "slices.f32", np.float32).reshape(S, Ny, Nx)
+    sizes = np.fromfile(dump / "sizes.i32", np.int32).reshape(S, 2)
+    T = np.fromfile(dump / "T.f32", np.float32).reshape(S, 4, 4).astype(np.float64)
+    sattrs = np.fromfile(dump / "slice_attrs.f64", np.float64).reshape(S, 18)
+    sidx = np.fromfile(dump / "stack_index.i32", np.int32)
+
+    # the reference, same order
+    rr = ri.Reconstruction()
+    stacks = [ri.Image.read(p) for p in names]
+    for im in stacks:
+        rr.add_stack(im, np.zeros(6), 2 * cfg.spacing)
+    mask = ri.Image.read(mp)
+    rr.call("crop_stack_to_mask", 0, mask.h)
+    rr.create_template(0, 1.0)
+    rr.set_mask(mask, 0.0)
+    rr.call("stack_registrations", 0)
+    m = rr.mask()
+    for i in (1, 2):
+        rr.call("crop_stack_to_mask", i, m.h)
+    rr.call("stack_registrations", 0)
+    rr.call("match_stack_intensities_with_masking", 700.0, 0)
+    rr.call("create_slices_and_transformations")
+    rr.call("mask_slices")
+    assert rr.num_slices() == S, (rr.num_slices(), S)
+    ref_dofs = rr.transformations()
+    worst_t = worst_a = worst_v = 0.0
+    for k in range(S):
+        rs = rr.slice(k)
+        worst_a = max(worst_a, float(np.abs(rs.attrs - sattrs[k]).max()))
+        worst_t = max(worst_t, float(np.abs(ri.rigid_matrix(ref_dofs[k]) - T[k]).max()))
+        sx, sy = sizes[k]
+        assert (int(rs.attrs[0]), int(rs.attrs[1])) == (sx, sy)
+        d = np.abs(rs.data[0] - slices[k, :sy, :sx].astype(np.float64))
+        worst_v = max(worst_v, float(d.max()))
+    # the registration moved stacks 1 and 2 back (their slices carry the inverse of the offset written into the headers)
+    moved = [np.abs(T[sidx == s][0] - np.eye(4)).max() for s in (0, 1, 2)]
+    assert moved[0] < 1e-9 and moved[1] > 0.5 and moved[2] > 0.5, moved
+    # geometry and transformations: float32 dump of double values; slice values: float32 of doubles around 700
+    assert worst_a <= 1e-9 and worst_t <= 2e-6 and worst_v <= 2e-4, (worst_a, worst_t, worst_v)

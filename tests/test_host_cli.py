@@ -102,7 +102,7 @@ def test_setup_pipeline_on_synthetic_stacks(cli, acquisition, tmp_path):
     a = acquisition
     out = tmp_path / "dump"
     out.mkdir()
-    r = run(cli, ["-o", "recon.nii.gz", "-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0",
+    r = run(cli, ["-o", "recon.nii.gz", "-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0", "--noStackRegistration",
                   "--dump_setup", str(out)], tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     idx = dict(line.split() for line in open(out / "index.txt"))
@@ -171,7 +171,7 @@ def test_dof_roundtrip_and_transformation_option(cli, acquisition, tmp_path):
     out = tmp_path / "dump"
     out.mkdir()
     r = run(cli, ["-o", "recon.nii.gz", "-i"] + a["names"][:2] + ["-t", "id", str(dof), "-m", a["mask_path"], "--resolution", "1.0",
-                  "--smooth_mask", "0", "--dump_setup", str(out)], tmp_path)
+                  "--smooth_mask", "0", "--noStackRegistration", "--dump_setup", str(out)], tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     S = int(dict(line.split() for line in open(out / "index.txt"))["S"])
     T = np.fromfile(out / "T.f32", np.float32).reshape(S, 4, 4).astype(np.float64)
