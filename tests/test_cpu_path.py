@@ -57,3 +57,43 @@ def test_cpu_path_reconstructs_the_phantom():
     err = {k: np.sqrt(np.mean((v[m] - truth) ** 2)) / np.sqrt(np.mean(truth ** 2)) for k, v in out.items()}
     assert np.isfinite(out["cpu_path"]).all()
     assert err["cpu_path"] < 0.25 and err["cpu_path"] < 2.5 * err["gpu_algorithm"], err
+
+
+def test_port_matches_the_reference_cpu_path_where_they_overlap():
+    """oracle/cpu_path.c against the reference's OWN CPU code (class irtkReconstruction in oracle/_ref/libref_irtk.so): CoeffInit +
+    GaussianReconstruction give the same volume (measured 3.5e-8 rms / 1.1e-6 max of the volume's RMS).  The remainder of the port's
+    iteration uses the GPU flavour of the robust statistics and regulariser (oracle/svr_oracle.c), the reference's CPU path its own:
+    after one outer iteration the two volumes are 2.6e-2 apart -- bench.py therefore times the reference library itself
+    (cpu_baseline.kind "reference") and keeps the port only as the fallback where that library is absent."""
+    import pytest
+    from types import SimpleNamespace
+    from oracle import ref_irtk as ri
+    if not ri.available():
+        pytest.skip("oracle/_ref/libref_irtk.so not built")
+    import bench
+    from fetalreconstruction_b200.pipeline import SVRPipeline, SVRParams, upload_dataset
+    from oracle import oracle as orc
+    from oracle.cpu_backend import CpuPathReconstruction
+    ds, _, _, _ = bench.svr_dataset(SimpleNamespace(workload="tiny"))
+    ri.set_threads(4)
+    r = ri.Reconstruction()
+    vol = bench.attrs18(ds.vol_attr)
+    r.set_reconstructed(ri.Image.new(vol))
+    r.set_mask(ri.Image.new(vol, ds.mask.astype(np.float64)), 0.0)
+    imgs = [ri.Image.new(bench.attrs18(a), ds.slices[k, :a.y, :a.x].astype(np.float64)) for k, a in enumerate(ds.slice_attrs)]
+    dofs = np.stack([ri.rigid_from_matrix(np.asarray(t, np.float64).reshape(4, 4)) for t in ds.trans])
+    r.set_slices(imgs, dofs, np.asarray(ds.stack_index, np.int32), np.asarray(ds.dims[:, 2], np.float64))
+    r.cpu_step("InitializeEM"); r.call("speedup", 1)
+    for name in ("InitializeEMValues", "CoeffInit", "GaussianReconstruction"):
+        r.cpu_step(name)
+    want = r.reconstructed().data
+    b = CpuPathReconstruction()
+    upload_dataset(b, ds)
+    p = SVRPipeline(b, ds.S, 0, ds.S, params=SVRParams(), host=orc)
+    p.InitializeEMGPU(ds.slices)
+    p.InitializeEMValuesGPU()
+    p.GaussianReconstructionGPU()
+    got = b.syncCPU().reshape(want.shape)
+    sc = np.sqrt(np.mean(want[want > 0] ** 2))
+    d = np.abs(got - want) / sc
+    assert np.sqrt(np.mean(d ** 2)) <= 1e-6 and d.max() <= 2e-5, (np.sqrt(np.mean(d ** 2)), d.max())
