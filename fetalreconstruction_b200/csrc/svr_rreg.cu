@@ -10,7 +10,7 @@
 //   irtkImageRegistrationWithPadding.cc:27-334 (per-level preparation: blur, resample, shift to >= 0, padding -> -1),
 //   irtkImageRigidRegistrationWithPadding.cc:110-205,304-402 (parameter guesses), :534-610 (Evaluate),
 //   include/irtkCrossCorrelationSimilarityMetric.h (CC on integer samples), image++/src/irtkGaussianBlurringWithPadding.cc,
-//   irtkConvolutionWithPadding_1D.cc:38-88, irtkResamplingWithPadding.cc:36-183, irtkResampling.cc:74-131,
+//   irtkConvolutionWithPadding_1D.cc:38-88, irtkResamplingWithPadding.cc:36-183,203-262,
 //   irtkLinearInterpolateImageFunction.cc:59-99, irtkBaseImage.cc:79-147, irtkHomogeneousTransformationIterator.h,
 //   packages/transformation/src/irtkRigidTransformation.cc:26-53.
 //
@@ -374,11 +374,12 @@ struct Engine {
         release(tmp);
         return 0;
     }
-    // irtkResamplingWithPadding<short>::Run + irtkResampling::Initialize (image++/src/irtkResampling.cc:74-131)
+    // irtkResamplingWithPadding<short>::Initialize + Run (image++/src/irtkResamplingWithPadding.cc:203-262): the new grid size is
+    // ROUNDED here (irtkResampling::Initialize truncates)
     int resample(DevImg& img, double rx, double ry, double rz, int padding)
     {
         Attr o = img.a;
-        int nx = int(img.a.x * img.a.dx / rx), ny = int(img.a.y * img.a.dy / ry), nz = int(img.a.z * img.a.dz / rz);
+        int nx = iround(img.a.x * img.a.dx / rx), ny = iround(img.a.y * img.a.dy / ry), nz = iround(img.a.z * img.a.dz / rz);
         if (nx < 1) { nx = 1; o.dx = img.a.dx; } else o.dx = rx;
         if (ny < 1) { ny = 1; o.dy = img.a.dy; } else o.dy = ry;
         if (nz < 1) { nz = 1; o.dz = img.a.dz; } else o.dz = rz;

@@ -20,11 +20,15 @@ from .geometry import ImageAttributes
 
 
 def resampled_attributes(attr: ImageAttributes, d: float) -> ImageAttributes:
-    """irtkResampling::Initialize (irtkResampling.cc:92-131): truncating grid, same origin / axes."""
-    nx = max(int(attr.x * attr.dx / d), 1)
-    ny = max(int(attr.y * attr.dy / d), 1)
-    nz = max(int(attr.z * attr.dz / d), 1)
-    return ImageAttributes(nx, ny, nz, d, d, d, np.array(attr.origin, float), attr.xaxis.copy(), attr.yaxis.copy(),
+    """irtkResamplingWithPadding::Initialize (irtkResamplingWithPadding.cc:203-262): the grid size is ROUNDED (irtkResampling's own
+    Initialize truncates), a dimension below 1 stays one voxel of the old size; same origin / axes.  (Round 1 truncated here, which
+    differs from the reference whenever thickness / voxel size is not an integer, e.g. 2.5 mm slices into a 1 mm volume.)"""
+    rnd = lambda v: int(v + 0.5) if v > 0 else int(v - 0.5)
+    n = [rnd(attr.x * attr.dx / d), rnd(attr.y * attr.dy / d), rnd(attr.z * attr.dz / d)]
+    old = [attr.dx, attr.dy, attr.dz]
+    size = [d if n[i] >= 1 else old[i] for i in range(3)]
+    n = [max(v, 1) for v in n]
+    return ImageAttributes(n[0], n[1], n[2], size[0], size[1], size[2], np.array(attr.origin, float), attr.xaxis.copy(), attr.yaxis.copy(),
                            attr.zaxis.copy())
 
 

@@ -147,6 +147,17 @@ ImageAttr resampled_attr(const ImageAttr& a, double dx, double dy, double dz)
     return r;
 }
 
+static int irtk_round(double x) { return x > 0 ? int(x + 0.5) : int(x - 0.5); }     // common++/include/irtkCommon.h:85-88
+ImageAttr resampled_attr_with_padding(const ImageAttr& a, double dx, double dy, double dz)
+{
+    ImageAttr r = a;
+    const int nx = irtk_round(a.x * a.dx / dx), ny = irtk_round(a.y * a.dy / dy), nz = irtk_round(a.z * a.dz / dz);
+    if (nx < 1) { r.x = 1; r.dx = a.dx; } else { r.x = nx; r.dx = dx; }
+    if (ny < 1) { r.y = 1; r.dy = a.dy; } else { r.y = ny; r.dy = dy; }
+    if (nz < 1) { r.z = 1; r.dz = a.dz; } else { r.z = nz; r.dz = dz; }
+    return r;
+}
+
 void transform_image_nn(const Image& source, const Rigid& t, Image& target, double target_padding, double source_padding)
 {
     const Mat4 m = source.a.world_to_image() * (t.matrix() * target.a.image_to_world());

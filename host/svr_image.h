@@ -70,6 +70,9 @@ struct Rigid {                                    // irtkRigidTransformation: tx
 
 // irtkResampling output grid: new_n = int(n * old / new) (min 1); origin and axes unchanged
 ImageAttr resampled_attr(const ImageAttr& a, double dx, double dy, double dz);
+// irtkResamplingWithPadding output grid (image++/src/irtkResamplingWithPadding.cc:203-262): new_n = round(n * old / new); a
+// dimension that would fall below 1 stays 1 voxel of the OLD size; origin and axes unchanged
+ImageAttr resampled_attr_with_padding(const ImageAttr& a, double dx, double dy, double dz);
 // irtkImageTransformation::Run with a nearest-neighbour interpolator, target padding -1, source padding 0:
 // resamples `source` onto the grid of `target` (whose values select the voxels to fill) through `t`
 void transform_image_nn(const Image& source, const Rigid& t, Image& target, double target_padding = -1, double source_padding = 0);

@@ -593,7 +593,7 @@ void Reconstruction::SyncCPU()
 // ---- irtkResamplingWithPadding (image++/src/irtkResamplingWithPadding.cc:36-183), z-plane 0 of a one-plane slice ------
 static Image resample_slice_with_padding(const Image& in, double d, double padding)
 {
-    Image out(resampled_attr(in.a, d, d, d), padding);
+    Image out(resampled_attr_with_padding(in.a, d, d, d), padding);
     const Mat4 m = in.a.world_to_image() * out.a.image_to_world();
     for (int k = 0; k < out.a.z; ++k) for (int j = 0; j < out.a.y; ++j) for (int i = 0; i < out.a.x; ++i) {
         double x = i, y = j, z = k;
@@ -629,7 +629,7 @@ void Reconstruction::PrepareRegistrationSlices()
     regW_ = regH_ = 0;
     int minx = INT_MAX, miny = INT_MAX;
     for (const Image& s : slices_) {
-        res_attrs_.push_back(resampled_attr(s.a, d, d, d));
+        res_attrs_.push_back(resampled_attr_with_padding(s.a, d, d, d));
         const ImageAttr& ra = res_attrs_.back();
         regW_ = std::max(regW_, ra.x); regH_ = std::max(regH_, ra.y);
         minx = std::min(minx, ra.x); miny = std::min(miny, ra.y);

@@ -126,7 +126,7 @@ def test_cli_registration_pass_uses_device_resampling(cli, acquisition, tmp_path
     device (svr_reg_resample_slices); --debug makes the host evaluate the same rules and print the largest difference."""
     a = acquisition
     r = run(cli, ["-o", "recon.nii.gz", "-i"] + a["names"] + ["-m", a["mask_path"], "--resolution", "1.0", "--smooth_mask", "0", "--noStackRegistration",
-                  "--iterations", "2", "--rec_iterations_first", "2", "--rec_iterations_last", "2", "--debug", "1", "--no_log", "1"], tmp_path)
+                  "--iterations", "2", "--rec_iterations_first", "2", "--rec_iterations_last", "2", "--debug", "1", "--no_log", "1", "--useGPUReg"], tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = [l for l in r.stdout.splitlines() if "device vs host resampling" in l]
     assert lines, r.stdout[-2000:]

@@ -112,13 +112,34 @@ def test_parameter_kernels_round_trip():
     assert np.allclose(mm.reshape(4, 4)[:3], rigid_matrix(*p1)[:3], atol=2e-6)
 
 
+def test_resampling_with_padding_matches_the_reference_irtk():
+    """registration.resampled_attributes / resample_plane0_with_padding against irtkResamplingWithPadding<irtkRealPixel> of the
+    reference's own IRTK (oracle/_ref/libref_irtk.so): grid (rounded size), geometry and plane 0 of the values."""
+    from oracle import ref_irtk as ri
+    if not ri.available():
+        pytest.skip("oracle/_ref/libref_irtk.so not built")
+    rng = np.random.default_rng(4)
+    for (nx, ny, dx, dz, d) in ((10, 8, 1.2, 2.5, 1.0), (33, 27, 1.1765, 2.5, 1.0), (16, 16, 0.75, 3.0, 0.75), (21, 19, 1.3, 4.0, 0.9)):
+        a = ImageAttributes(nx, ny, 1, dx, dx, dz, rng.uniform(-20, 20, 3))
+        img = rng.uniform(1, 900, (ny, nx))
+        img[:, : nx // 3] = -1.0
+        img[ny // 2, nx // 2] = -1.0
+        ra = resampled_attributes(a, d)
+        ref = ri.Image.new(np.concatenate([[nx, ny, 1, dx, dx, dz], a.origin, a.xaxis, a.yaxis, a.zaxis]), img[None]).resample_with_padding(d, d, d, -1)
+        got_attr = np.concatenate([[ra.x, ra.y, ra.z, ra.dx, ra.dy, ra.dz], ra.origin, ra.xaxis, ra.yaxis, ra.zaxis])
+        np.testing.assert_allclose(got_attr, ref.attrs, rtol=0, atol=1e-12)
+        out = resample_plane0_with_padding(img, a, ra)
+        np.testing.assert_array_equal(out == -1, ref.data[0] == -1)
+        np.testing.assert_allclose(out, ref.data[0], rtol=2e-7, atol=0)      # the restatement returns float32 (what the device is fed)
+
+
 def test_resampling_with_padding_rules():
     a = ImageAttributes(10, 8, 1, 1.2, 1.2, 2.5)
     ra = resampled_attributes(a, 1.0)
-    assert (ra.x, ra.y, ra.z) == (12, 9, 2)               # int(n * old / new)
+    assert (ra.x, ra.y, ra.z) == (12, 10, 3)              # round(n * old / new): irtkResamplingWithPadding.cc:217-219
     img = np.full((8, 10), 7.0, np.float32)
     out = resample_plane0_with_padding(img, a, ra)
-    assert out.shape == (9, 12)
+    assert out.shape == (10, 12)
     inner = out[1:-1, 1:-1]
     assert np.allclose(inner[inner != -1], 7.0)           # renormalised weights keep a constant
     img[:, :5] = -1.0
