@@ -568,11 +568,18 @@ reg_resample_kernel(int S, int W, int H, int Nx, int Ny, const float* __restrict
     const int j = pix / W, i = pix - j * W;
     if (i >= out_sizes[2 * s] || j >= out_sizes[2 * s + 1]) { out[idx] = -1.0f; return; }
     const int ax = in_sizes[2 * s], ay = in_sizes[2 * s + 1];
-    const double* q = m + 12 * (size_t)s;
-    const double di = (double)i, dj = (double)j;
-    const double x = __dadd_rn(__dadd_rn(__dmul_rn(q[0], di), __dmul_rn(q[1], dj)), q[3]);
-    const double y = __dadd_rn(__dadd_rn(__dmul_rn(q[4], di), __dmul_rn(q[5], dj)), q[7]);
-    const double z = __dadd_rn(__dadd_rn(__dmul_rn(q[8], di), __dmul_rn(q[9], dj)), q[11]);
+    // the reference maps the output voxel to world (ImageToWorld of the resampled slice) and then into the input image
+    // (WorldToImage of the slice), two separately rounded matrix-vector products (image++/include/irtkBaseImage.h:425-468):
+    // on grids that coincide the coordinates are integers up to rounding, and floor() must fall as it does there
+    const double* q = m + 24 * (size_t)s;
+    const double* p = q + 12;
+    const double di = (double)i, dj = (double)j, dk = 0.0;
+    const double wx_ = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[0], di), __dmul_rn(q[1], dj)), __dmul_rn(q[2], dk)), q[3]);
+    const double wy_ = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[4], di), __dmul_rn(q[5], dj)), __dmul_rn(q[6], dk)), q[7]);
+    const double wz_ = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[8], di), __dmul_rn(q[9], dj)), __dmul_rn(q[10], dk)), q[11]);
+    const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(p[0], wx_), __dmul_rn(p[1], wy_)), __dmul_rn(p[2], wz_)), p[3]);
+    const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(p[4], wx_), __dmul_rn(p[5], wy_)), __dmul_rn(p[6], wz_)), p[7]);
+    const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(p[8], wx_), __dmul_rn(p[9], wy_)), __dmul_rn(p[10], wz_)), p[11]);
     const double fu = floor(x), fv = floor(y), fw = floor(z);
     const int u = (int)fu, v = (int)fv, w = (int)fw;
     const double dx = __dadd_rn(x, -fu), dy = __dadd_rn(y, -fv), dz = __dadd_rn(z, -fw);
@@ -618,9 +625,9 @@ int svr_reg_resample_slices(svr_context* c, const double* src_from_out, const in
     SVR_CUDA(c, cudaSetDevice(c->device));
     double* d_m = nullptr;
     int* d_sz = nullptr;
-    SVR_CUDA(c, cudaMalloc(&d_m, sizeof(double) * 12 * S));
+    SVR_CUDA(c, cudaMalloc(&d_m, sizeof(double) * 24 * S));
     if (cudaMalloc(&d_sz, sizeof(int) * 4 * S) != cudaSuccess) { cudaFree(d_m); c->err = "svr_reg_resample_slices: out of device memory"; return 1; }
-    cudaMemcpyAsync(d_m, src_from_out, sizeof(double) * 12 * S, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_m, src_from_out, sizeof(double) * 24 * S, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(d_sz, in_sizes, sizeof(int) * 2 * S, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(d_sz + 2 * S, out_sizes, sizeof(int) * 2 * S, cudaMemcpyHostToDevice, c->stream);
     if (slices_resampled_i2w)

@@ -240,10 +240,12 @@ class Reconstruction:
         m = None if slices_resampledI2W is None else _f32(slices_resampledI2W, (self.regS, 16))
         self._ck(self._lib.svr_reg_fill_slices(self._h, _p(cube), _p(m)))
 
-    def resampleRegSlices(self, src_from_out, in_sizes, out_sizes, slices_resampledI2W=None):
+    def resampleRegSlices(self, out_i2w, in_w2i, in_sizes, out_sizes, slices_resampledI2W=None):
         """Device form of PrepareRegistrationSlices' resampling (svr_reg_resample_slices): the slices uploaded by
-        FillSlices are resampled on the device into the registration cube.  src_from_out [S,4,4] float64."""
-        m = np.ascontiguousarray(np.asarray(src_from_out, np.float64).reshape(self.regS, 4, 4)[:, :3, :].reshape(self.regS, 12))
+        FillSlices are resampled on the device into the registration cube.  out_i2w / in_w2i [S,4,4] float64: the resampled
+        slice's image-to-world and the slice's world-to-image matrices."""
+        m = np.ascontiguousarray(np.concatenate([np.asarray(out_i2w, np.float64).reshape(self.regS, 4, 4)[:, :3, :].reshape(self.regS, 12),
+                                                 np.asarray(in_w2i, np.float64).reshape(self.regS, 4, 4)[:, :3, :].reshape(self.regS, 12)], 1))
         a = np.ascontiguousarray(in_sizes, np.int32).reshape(self.regS, 2)
         o = np.ascontiguousarray(out_sizes, np.int32).reshape(self.regS, 2)
         i2w = None if slices_resampledI2W is None else _f32(slices_resampledI2W, (self.regS, 16))

@@ -38,11 +38,17 @@ def resample_plane0_with_padding(img: np.ndarray, attr: ImageAttributes, out_att
     (irtkResamplingWithPadding.cc:36-183): neighbours equal to the padding value are dropped and the
     remaining weights renormalised; out-of-bounds neighbours count as not padded but add nothing; the
     result is padding when >= 4 of the 8 neighbours are padding or the weight sum is 0."""
-    m = attr.world_to_image() @ out_attr.image_to_world()
+    # two matrix-vector products in the reference's order (ImageToWorld of the output, then WorldToImage of the input): on
+    # coinciding grids the coordinates are integers up to rounding and floor() has to fall as it does there
+    a, b = out_attr.image_to_world(), attr.world_to_image()
     j, i = np.meshgrid(np.arange(out_attr.y, dtype=np.float64), np.arange(out_attr.x, dtype=np.float64), indexing="ij")
-    x = m[0, 0] * i + m[0, 1] * j + m[0, 3]
-    y = m[1, 0] * i + m[1, 1] * j + m[1, 3]
-    z = m[2, 0] * i + m[2, 1] * j + m[2, 3]
+    k = np.zeros_like(i)
+    wx = a[0, 0] * i + a[0, 1] * j + a[0, 2] * k + a[0, 3]
+    wy = a[1, 0] * i + a[1, 1] * j + a[1, 2] * k + a[1, 3]
+    wz = a[2, 0] * i + a[2, 1] * j + a[2, 2] * k + a[2, 3]
+    x = b[0, 0] * wx + b[0, 1] * wy + b[0, 2] * wz + b[0, 3]
+    y = b[1, 0] * wx + b[1, 1] * wy + b[1, 2] * wz + b[1, 3]
+    z = b[2, 0] * wx + b[2, 1] * wy + b[2, 2] * wz + b[2, 3]
     u, v, w = np.floor(x).astype(int), np.floor(y).astype(int), np.floor(z).astype(int)
     dx, dy, dz = x - u, y - v, z - w
     val = np.zeros_like(x)
@@ -85,8 +91,9 @@ class RegistrationFrontEnd:
             # the CUDA backend resamples the slices it already holds (FillSlices) on the device
             if not slices_resident and S:
                 backend.FillSlices(np.asarray(slices).ravel())
-            m = np.stack([a.world_to_image() @ ra.image_to_world() for a, ra in zip(slice_attrs, self.res_attrs)]) if S else np.zeros((0, 4, 4))
-            backend.resampleRegSlices(m, [(a.x, a.y) for a in slice_attrs], [(ra.x, ra.y) for ra in self.res_attrs], i2w)
+            mo = np.stack([ra.image_to_world() for ra in self.res_attrs]) if S else np.zeros((0, 4, 4))
+            mi = np.stack([a.world_to_image() for a in slice_attrs]) if S else np.zeros((0, 4, 4))
+            backend.resampleRegSlices(mo, mi, [(a.x, a.y) for a in slice_attrs], [(ra.x, ra.y) for ra in self.res_attrs], i2w)
         else:
             # the CPU twins (oracle, reference adapter: test infrastructure) take the host-resampled cube
             self._cube = self.resample_on_host(slices, slice_attrs)

@@ -594,10 +594,11 @@ void Reconstruction::SyncCPU()
 static Image resample_slice_with_padding(const Image& in, double d, double padding)
 {
     Image out(resampled_attr_with_padding(in.a, d, d, d), padding);
-    const Mat4 m = in.a.world_to_image() * out.a.image_to_world();
+    const Mat4 mo = out.a.image_to_world(), mi = in.a.world_to_image();     // applied one after the other, as the reference does
     for (int k = 0; k < out.a.z; ++k) for (int j = 0; j < out.a.y; ++j) for (int i = 0; i < out.a.x; ++i) {
         double x = i, y = j, z = k;
-        m.apply(x, y, z);
+        mo.apply(x, y, z);
+        mi.apply(x, y, z);
         const int u = (int)std::floor(x), v = (int)std::floor(y), w = (int)std::floor(z);
         const double fx = x - u, fy = y - v, fz = z - w;
         double val = 0, wsum = 0;
@@ -636,12 +637,12 @@ void Reconstruction::PrepareRegistrationSlices()
     }
     const double waste = ((double)(regW_ - minx) * (regH_ - miny) * S) * sizeof(double) * 5.0 / 1024.0;
     std::printf("GPU memory waste approx RegSlices: %f KB with %d %d %d %d\n", waste, regW_, regH_, minx, miny);
-    std::vector<double> m(12 * (size_t)S);
+    std::vector<double> m(24 * (size_t)S);
     std::vector<int> in_sizes(2 * (size_t)S), out_sizes(2 * (size_t)S);
     std::vector<float> i2w(16 * (size_t)S);
     for (int n = 0; n < S; ++n) {
-        const Mat4 mm = slices_[n].a.world_to_image() * res_attrs_[n].image_to_world();
-        for (int r = 0; r < 3; ++r) for (int q = 0; q < 4; ++q) m[12 * (size_t)n + 4 * r + q] = mm.m[r][q];
+        const Mat4 mo = res_attrs_[n].image_to_world(), mi = slices_[n].a.world_to_image();
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 4; ++q) { m[24 * (size_t)n + 4 * r + q] = mo.m[r][q]; m[24 * (size_t)n + 12 + 4 * r + q] = mi.m[r][q]; }
         in_sizes[2 * n] = slices_[n].a.x; in_sizes[2 * n + 1] = slices_[n].a.y;
         out_sizes[2 * n] = res_attrs_[n].x; out_sizes[2 * n + 1] = res_attrs_[n].y;
         res_attrs_[n].image_to_world().to_float16(&i2w[16 * n]);
@@ -650,7 +651,7 @@ void Reconstruction::PrepareRegistrationSlices()
         const int Sl = (int)r.idx.size();
         RCK(r, svr_reg_init_storage(r.c, regW_, regH_, Sl, (float)d, (float)d, (float)d), "initRegStorageVolumes");
         if (Sl == 0) return;
-        const std::vector<double> ml = take(r, m, 12);
+        const std::vector<double> ml = take(r, m, 24);
         const std::vector<int> is = take(r, in_sizes, 2), os = take(r, out_sizes, 2);
         const std::vector<float> il = take(r, i2w, 16);
         RCK(r, svr_reg_resample_slices(r.c, ml.data(), is.data(), os.data(), il.data()), "resampleRegSlices");

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SVR_ABI_VERSION 1
+#define SVR_ABI_VERSION 2
 
 typedef struct svr_context svr_context;
 
@@ -150,7 +150,8 @@ int svr_reg_fill_slices(svr_context *ctx, const float *cube, const float *slices
  * irtkResamplingWithPadding (IRTKSimple2/image++/src/irtkResamplingWithPadding.cc:36-183, padding -1) on the host and
  * uploads the result.  Here the slices uploaded by svr_fill_slices are resampled in place on the device, in double
  * precision and in the reference's order of operations, into the registration cube of svr_reg_init_storage:
- *   src_from_out [S][12]  rows 0..2 of (slice world-to-image) x (resampled slice image-to-world), double
+ *   src_from_out [S][24]  rows 0..2 of the resampled slice's image-to-world matrix, then rows 0..2 of the slice's world-to-image
+ *                         matrix (double): applied one after the other like the reference's ImageToWorld / WorldToImage calls
  *   in_sizes     [S][2]   valid extent (x, y) of slice s inside the packed slice cube
  *   out_sizes    [S][2]   extent (x, y) of the resampled slice; the rest of its [H][W] plane is padding
  * Equivalent to svr_reg_fill_slices with the host-resampled cube. */

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 
 def test_abi_version(built_lib):
-    assert _lib.load().svr_abi_version() == 1
+    assert _lib.load().svr_abi_version() == 2
 
 
 def test_create_fails_loudly_without_gpu(built_lib):

@@ -138,16 +138,16 @@ def test_device_resampling_matches_host_rules_on_ragged_padded_slices():
     g.initStorageVolumes((Nx, Ny, S))
     g.FillSlices(cube.ravel())
     g.initRegStorageVolumes((W, H, S), (d, d, d))
-    m = np.stack([a.world_to_image() @ r.image_to_world() for a, r in zip(attrs, res)])
-    g.resampleRegSlices(m, [(a.x, a.y) for a in attrs], [(r.x, r.y) for r in res])
+    m = (np.stack([r.image_to_world() for r in res]), np.stack([a.world_to_image() for a in attrs]))
+    g.resampleRegSlices(*m, [(a.x, a.y) for a in attrs], [(r.x, r.y) for r in res])
     got = g.debugRegSlices()
     assert (want != -1).sum() > 500 and ((want == -1) & (np.arange(W)[None, None, :] < np.array([r.x for r in res])[:, None, None])).sum() > 50
     assert np.array_equal(got, want)
     with pytest.raises(SVRError):                                              # extent outside the slice cube
-        g.resampleRegSlices(m, [(Nx + 1, Ny)] * S, [(r.x, r.y) for r in res])
+        g.resampleRegSlices(*m, [(Nx + 1, Ny)] * S, [(r.x, r.y) for r in res])
     with pytest.raises(SVRError):                                              # extent outside the registration cube
-        g.resampleRegSlices(m, [(a.x, a.y) for a in attrs], [(W + 1, H)] * S)
+        g.resampleRegSlices(*m, [(a.x, a.y) for a in attrs], [(W + 1, H)] * S)
     g2 = Reconstruction(0)
     g2.regS, g2.regW, g2.regH = S, W, H
     with pytest.raises(SVRError):                                              # no registration storage yet
-        g2.resampleRegSlices(m, [(a.x, a.y) for a in attrs], [(r.x, r.y) for r in res])
+        g2.resampleRegSlices(*m, [(a.x, a.y) for a in attrs], [(r.x, r.y) for r in res])
