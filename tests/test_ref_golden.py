@@ -94,7 +94,9 @@ def test_oracle_matches_reference_svr_loop():
 
 def test_oracle_matches_reference_registration():
     got, ref = mg.reg_case(), _ref("reg")
-    assert float(got["resampled_checksum"]) == pytest.approx(float(ref["resampled_checksum"]), rel=1e-12)
+    # the cube the reference was run on came from round 1's resampling (pre-multiplied matrices); the reference-order resampling of
+    # round 2 moves a handful of its float32 voxels by an ulp (4e-11 of the sum)
+    assert float(got["resampled_checksum"]) == pytest.approx(float(ref["resampled_checksum"]), rel=1e-9)
     for k in ("sim_level0", "sim_level1"):
         assert np.abs(got[k] - ref[k]).max() <= 2e-3, (k, np.abs(got[k] - ref[k]).max())
     # the optimiser walks a similarity staircase whose steps depend on the texture filter's arithmetic: the oracle
