@@ -45,6 +45,7 @@ struct M4 { double m[4][4]; };
 Attr attr_from18(const double* a)
 {
     Attr t;
+    memset(&t, 0, sizeof t);                   // padding bytes too: Attr is compared bytewise when images are grouped
     t.x = (int)a[0]; t.y = (int)a[1]; t.z = (int)a[2]; t.dx = a[3]; t.dy = a[4]; t.dz = a[5];
     for (int i = 0; i < 3; ++i) { t.o[i] = a[6 + i]; t.ax[i] = a[9 + i]; t.ay[i] = a[12 + i]; t.az[i] = a[15 + i]; }
     return t;
@@ -107,10 +108,12 @@ M4 rigid_of(const double* d)
 }
 inline int iround(double x) { return x > 0 ? int(x + 0.5) : int(x - 0.5); }      // common++/include/irtkCommon.h:85-88
 
-struct DevImg {
+struct DevImg {                      // nb images of identical geometry, back to back
     short* d = nullptr;
     Attr a{};
+    int nb = 1;
     size_t n() const { return (size_t)a.x * a.y * a.z; }
+    size_t total() const { return n() * (size_t)nb; }
 };
 
 }  // namespace
@@ -129,12 +132,13 @@ __device__ __forceinline__ short put_as_double_short(double v)
 }
 
 // irtkConvolutionWithPadding_1D<short>::Run(x, y, z, t) with normalisation, along `axis` (image++/src/irtkConvolutionWithPadding_1D.cc:38-88)
-__global__ void rreg_blur_kernel(const short* __restrict__ in, short* __restrict__ out, int X, int Y, int Z, int axis,
+__global__ void rreg_blur_kernel(const short* __restrict__ in, short* __restrict__ out, int X, int Y, int Z, int nb, int axis,
                                  const double* __restrict__ kern, int n, int padding)
 {
-    const size_t N = (size_t)X * Y * Z;
+    // nb images of X x Y x Z voxels back to back: voxel index within the batch = image * XYZ + (z * Y + y) * X + x
+    const size_t N = (size_t)X * Y * Z * nb;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < N; idx += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % X), y = (int)((idx / X) % Y), z = (int)(idx / ((size_t)X * Y));
+        const int x = (int)(idx % X), y = (int)((idx / X) % Y), z = (int)((idx / ((size_t)X * Y)) % Z);
         if ((int)in[idx] <= padding) { out[idx] = (short)padding; continue; }
         const int c0 = axis == 0 ? x : (axis == 1 ? y : z), dim = axis == 0 ? X : (axis == 1 ? Y : Z);
         const size_t stride = axis == 0 ? 1 : (axis == 1 ? (size_t)X : (size_t)X * Y);
@@ -162,12 +166,14 @@ __device__ __forceinline__ void apply34(const Mat34& M, double& x, double& y, do
 }
 
 // irtkMultiThreadedResamplingWithPadding (image++/src/irtkResamplingWithPadding.cc:36-183)
-__global__ void rreg_resample_kernel(const short* __restrict__ in, int X, int Y, int Z, short* __restrict__ out, int OX, int OY, int OZ,
-                                     Mat34 out_i2w, Mat34 in_w2i, int padding)
+__global__ void rreg_resample_kernel(const short* __restrict__ in_all, int X, int Y, int Z, short* __restrict__ out, int OX, int OY, int OZ,
+                                     int nb, Mat34 out_i2w, Mat34 in_w2i, int padding)
 {
-    const size_t N = (size_t)OX * OY * OZ;
+    const size_t ON = (size_t)OX * OY * OZ, N = ON * nb;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < N; idx += (size_t)gridDim.x * blockDim.x) {
-        const int i = (int)(idx % OX), j = (int)((idx / OX) % OY), k = (int)(idx / ((size_t)OX * OY));
+        const size_t loc = idx % ON;
+        const short* in = in_all + (idx / ON) * ((size_t)X * Y * Z);
+        const int i = (int)(loc % OX), j = (int)((loc / OX) % OY), k = (int)(loc / ((size_t)OX * OY));
         double x = i, y = j, z = k;
         apply34(out_i2w, x, y, z);
         apply34(in_w2i, x, y, z);
@@ -194,20 +200,28 @@ __global__ void rreg_resample_kernel(const short* __restrict__ in, int X, int Y,
     }
 }
 
+// per-image range over voxels > padding: grid = (chunks, images)
 __global__ void rreg_minmax_kernel(const short* __restrict__ in, size_t N, int padding, int* __restrict__ mm)
 {
+    const short* img = in + (size_t)blockIdx.y * N;
     int mn = INT_MAX, mx = INT_MIN;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < N; idx += (size_t)gridDim.x * blockDim.x) {
-        const int v = in[idx];
+        const int v = img[idx];
         if (v > padding) { mn = min(mn, v); mx = max(mx, v); }
     }
     for (int o = 16; o; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[0], mn); atomicMax(&mm[1], mx); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[2 * blockIdx.y], mn); atomicMax(&mm[2 * blockIdx.y + 1], mx); }
+}
+__global__ void rreg_fill_minmax_kernel(int* __restrict__ mm, int nb)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nb) { mm[2 * i] = INT_MAX; mm[2 * i + 1] = INT_MIN; }
 }
 // irtkImageRegistrationWithPadding::Initialize(level): voxels > padding -> value - min, others -> -1
-__global__ void rreg_shift_kernel(short* __restrict__ img, size_t N, int padding, const int* __restrict__ mm)
+__global__ void rreg_shift_kernel(short* __restrict__ in, size_t N, int padding, const int* __restrict__ mm)
 {
-    const int mn = mm[0];
+    short* img = in + (size_t)blockIdx.y * N;
+    const int mn = mm[2 * blockIdx.y];
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < N; idx += (size_t)gridDim.x * blockDim.x) {
         const int v = img[idx];
         img[idx] = v > padding ? (short)(v - mn) : (short)-1;
@@ -345,7 +359,7 @@ struct Engine {
     int blur(DevImg& img, double sigma, int padding)
     {
         short* tmp = nullptr;
-        if (alloc(&tmp, img.n())) return 1;
+        if (alloc(&tmp, img.total())) return 1;
         const double vox[3] = { img.a.dx, img.a.dy, img.a.dz };
         const int dims[3] = { img.a.x, img.a.y, img.a.z };
         for (int axis = 0; axis < 3; ++axis) {
@@ -365,7 +379,7 @@ struct Engine {
             if (alloc(&dk, n)) return 1;
             SVR_CUDA(c, cudaMemcpyAsync(dk, k.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             SVR_CUDA(c, cudaStreamSynchronize(c->stream));
-            rreg_blur_kernel<<<grid(img.n()), 256, 0, c->stream>>>(img.d, tmp, img.a.x, img.a.y, img.a.z, axis, dk, n, padding);
+            rreg_blur_kernel<<<grid(img.total()), 256, 0, c->stream>>>(img.d, tmp, img.a.x, img.a.y, img.a.z, img.nb, axis, dk, n, padding);
             SVR_KERNEL_CHECK(c);
             std::swap(img.d, tmp);
             SVR_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -385,9 +399,9 @@ struct Engine {
         if (nz < 1) { nz = 1; o.dz = img.a.dz; } else o.dz = rz;
         o.x = nx; o.y = ny; o.z = nz;
         short* out = nullptr;
-        if (alloc(&out, (size_t)nx * ny * nz)) return 1;
-        rreg_resample_kernel<<<grid((size_t)nx * ny * nz), 256, 0, c->stream>>>(img.d, img.a.x, img.a.y, img.a.z, out, nx, ny, nz, to34(i2w_of(o)),
-                                                                                 to34(w2i_of(img.a)), padding);
+        if (alloc(&out, (size_t)nx * ny * nz * img.nb)) return 1;
+        rreg_resample_kernel<<<grid((size_t)nx * ny * nz * img.nb), 256, 0, c->stream>>>(img.d, img.a.x, img.a.y, img.a.z, out, nx, ny, nz, img.nb,
+                                                                                          to34(i2w_of(o)), to34(w2i_of(img.a)), padding);
         SVR_KERNEL_CHECK(c);
         SVR_CUDA(c, cudaStreamSynchronize(c->stream));
         release(img.d);
@@ -398,23 +412,31 @@ struct Engine {
     int shift(DevImg& img, int padding)
     {
         int* mm = nullptr;
-        if (alloc(&mm, 2)) return 1;
-        const int init[2] = { INT_MAX, INT_MIN };
-        SVR_CUDA(c, cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
-        rreg_minmax_kernel<<<grid(img.n()), 256, 0, c->stream>>>(img.d, img.n(), padding, mm);
+        if (alloc(&mm, 2 * (size_t)img.nb)) return 1;
+        rreg_fill_minmax_kernel<<<(img.nb + 255) / 256, 256, 0, c->stream>>>(mm, img.nb);
         SVR_KERNEL_CHECK(c);
-        rreg_shift_kernel<<<grid(img.n()), 256, 0, c->stream>>>(img.d, img.n(), padding, mm);
+        const int chunks = (int)std::min<size_t>((img.n() + 1023) / 1024, 64);
+        for (int b0 = 0; b0 < img.nb; b0 += 65535) {            // gridDim.y limit
+            const dim3 g(std::max(chunks, 1), std::min(img.nb - b0, 65535));
+            rreg_minmax_kernel<<<g, 256, 0, c->stream>>>(img.d + (size_t)b0 * img.n(), img.n(), padding, mm + 2 * b0);
+            SVR_KERNEL_CHECK(c);
+            rreg_shift_kernel<<<g, 256, 0, c->stream>>>(img.d + (size_t)b0 * img.n(), img.n(), padding, mm + 2 * b0);
+            SVR_KERNEL_CHECK(c);
+        }
         SVR_KERNEL_CHECK(c);
         SVR_CUDA(c, cudaStreamSynchronize(c->stream));
         release(mm);
         return 0;
     }
-    // one image of one level: a copy of the original, blurred, resampled when the level asks for it, shifted
-    int prepare(const short* host, const Attr& a, double blur_sigma, const double res0[3], const double res[3], int level, int padding, DevImg& out)
+    // the images of one group (identical geometry and parameters) at one level: copies of the originals, blurred, resampled when
+    // the level asks for it, shifted -- one set of launches for the whole group
+    int prepare(const std::vector<const short*>& host, const Attr& a, double blur_sigma, const double res0[3], const double res[3], int level, int padding,
+                DevImg& out)
     {
-        out.a = a;
-        if (alloc(&out.d, out.n())) return 1;
-        SVR_CUDA(c, cudaMemcpyAsync(out.d, host, out.n() * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+        out.a = a; out.nb = (int)host.size();
+        if (alloc(&out.d, out.total())) return 1;
+        for (size_t q = 0; q < host.size(); ++q)
+            SVR_CUDA(c, cudaMemcpyAsync(out.d + q * out.n(), host[q], out.n() * sizeof(short), cudaMemcpyHostToDevice, c->stream));
         SVR_CUDA(c, cudaStreamSynchronize(c->stream));
         if (blur_sigma > 0 && blur(out, blur_sigma, padding)) return 1;
         const double temp = fabs(res0[0] - a.dx) + fabs(res0[1] - a.dy) + fabs(res0[2] - a.dz);
@@ -501,6 +523,7 @@ int svr_rreg_blur_with_padding(svr_context* c, const short* voxels, const double
     DevImg img; img.a = attr_from18(attr18);
     if (e.alloc(&img.d, img.n())) return 1;
     SVR_CUDA(c, cudaMemcpyAsync(img.d, voxels, img.n() * sizeof(short), cudaMemcpyHostToDevice, c->stream));
+    SVR_CUDA(c, cudaStreamSynchronize(c->stream));
     if (e.blur(img, sigma, padding)) return 1;
     SVR_CUDA(c, cudaMemcpyAsync(out, img.d, img.n() * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
     SVR_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -559,11 +582,15 @@ int svr_rreg_register(svr_context* c, int n_items, int n_images, const short* co
     for (int level = 2; level >= 0; --level) {
         if (level_only >= 0 && level != level_only) continue;
         Engine e{ c };
-        // prepare every distinct (image, role, parameters) once: key = (image, role, padding, blur, resolution)
+        // Prepare every distinct (image, role, parameters) once; images that share geometry and parameters (the patches of a stack,
+        // the slices of a stack) form a GROUP that is filtered by one set of launches.
         struct Key { int img, role, pad; double blur, r0, r1, r2, q0, q1, q2; bool operator<(const Key& o) const { return memcmp(this, &o, sizeof(Key)) < 0; } };
-        std::map<Key, int> index;
-        std::vector<DevImg> prepared;
-        std::vector<int> tprep(n_items), sprep(n_items);
+        struct GKey { int role, pad; double blur, r0, r1, r2, q0, q1, q2; Attr a; bool operator<(const GKey& o) const { return memcmp(this, &o, sizeof(GKey)) < 0; } };
+        std::map<Key, std::pair<int, int>> index;            // -> (group, position in the group)
+        std::map<GKey, int> gindex;
+        std::vector<GKey> gkeys;
+        std::vector<std::vector<const short*>> ghost;
+        std::vector<std::pair<int, int>> tprep(n_items), sprep(n_items);
         for (int i = 0; i < n_items; ++i) {
             const RegParams& p = params[i];
             for (int role = 0; role < 2; ++role) {
@@ -574,24 +601,32 @@ int svr_rreg_register(svr_context* c, int n_items, int n_images, const short* co
                 const double* r0 = role == 0 ? p.tres[0] : p.sres[0];
                 k.r0 = r[0]; k.r1 = r[1]; k.r2 = r[2]; k.q0 = r0[0]; k.q1 = r0[1]; k.q2 = r0[2];
                 auto f = index.find(k);
-                int id;
                 if (f == index.end()) {
-                    DevImg d;
-                    const double res0[3] = { k.q0, k.q1, k.q2 }, res[3] = { k.r0, k.r1, k.r2 };
-                    if (e.prepare(voxels[img], attr[img], k.blur, res0, res, level, k.pad, d)) return 1;
-                    id = (int)prepared.size();
-                    prepared.push_back(d);
-                    index[k] = id;
-                } else id = f->second;
-                (role == 0 ? tprep : sprep)[i] = id;
+                    GKey g; memset(&g, 0, sizeof g);
+                    g.role = role; g.pad = k.pad; g.blur = k.blur; g.r0 = k.r0; g.r1 = k.r1; g.r2 = k.r2; g.q0 = k.q0; g.q1 = k.q1; g.q2 = k.q2;
+                    memcpy(&g.a, &attr[img], sizeof(Attr));
+                    auto gf = gindex.find(g);
+                    int gid;
+                    if (gf == gindex.end()) { gid = (int)gkeys.size(); gindex[g] = gid; gkeys.push_back(g); ghost.emplace_back(); }
+                    else gid = gf->second;
+                    ghost[gid].push_back(voxels[img]);
+                    f = index.emplace(k, std::make_pair(gid, (int)ghost[gid].size() - 1)).first;
+                }
+                (role == 0 ? tprep : sprep)[i] = f->second;
             }
         }
+        std::vector<DevImg> prepared(gkeys.size());
+        for (size_t g = 0; g < gkeys.size(); ++g) {
+            const GKey& k = gkeys[g];
+            const double res0[3] = { k.q0, k.q1, k.q2 }, res[3] = { k.r0, k.r1, k.r2 };
+            if (e.prepare(ghost[g], k.a, k.blur, res0, res, level, k.pad, prepared[g])) return 1;
+        }
         if (level_only >= 0) {
-            auto dump = [&](int id, short* out, double* a18) -> int {
+            auto dump = [&](std::pair<int, int> id, short* out, double* a18) -> int {
                 if (!out) return 0;
-                const DevImg& d = prepared[id];
+                const DevImg& d = prepared[id.first];
                 if (d.n() > prepared_capacity) { c->err = "svr_rreg_register: prepared-image buffer too small"; return 2; }
-                SVR_CUDA(c, cudaMemcpyAsync(out, d.d, d.n() * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+                SVR_CUDA(c, cudaMemcpyAsync(out, d.d + (size_t)id.second * d.n(), d.n() * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
                 SVR_CUDA(c, cudaStreamSynchronize(c->stream));
                 if (a18) attr_to18(d.a, a18);
                 return 0;
@@ -615,11 +650,11 @@ int svr_rreg_register(svr_context* c, int n_items, int n_images, const short* co
             int rows = 0;
             for (size_t a = 0; a < active.size(); ++a) {
                 const int i = active[a];
-                const DevImg& t = prepared[tprep[i]]; const DevImg& s = prepared[sprep[i]];
+                const DevImg& t = prepared[tprep[i].first]; const DevImg& s = prepared[sprep[i].first];
                 EvalItem& it = h_items[a];
-                it.tgt = t.d; it.src = s.d; it.tx = t.a.x; it.ty = t.a.y; it.tz = t.a.z; it.sx = s.a.x; it.sy = s.a.y; it.sz = s.a.z;
+                it.tgt = t.d + (size_t)tprep[i].second * t.n(); it.src = s.d + (size_t)sprep[i].second * s.n(); it.tx = t.a.x; it.ty = t.a.y; it.tz = t.a.z; it.sx = s.a.x; it.sy = s.a.y; it.sz = s.a.z;
                 it.row0 = rows; rows += t.a.y * t.a.z;
-                const M4 m = mul(mul(sw2i[sprep[i]], rigid_of(opt[i].dof)), ti2w[tprep[i]]);      // (W2I * T) * I2W
+                const M4 m = mul(mul(sw2i[sprep[i].first], rigid_of(opt[i].dof)), ti2w[tprep[i].first]);      // (W2I * T) * I2W
                 for (int r = 0; r < 3; ++r) for (int q = 0; q < 4; ++q) it.m[4 * r + q] = m.m[r][q];
             }
             const int na = (int)active.size();

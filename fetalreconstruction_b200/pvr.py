@@ -354,6 +354,51 @@ class PVRPipeline:
         return self.b.recon_copyToHost()
 
 
+class PatchRegistration:
+    """The patch-to-volume registration PVRreconstructionGPU runs between iterations: patchBased2D3DRegistration<T>::runHybrid
+    (patchBased2D3DRegistration.cpp:88-223) registers every patch with IRTK's irtkImageRigidRegistrationWithPadding on the CPU
+    (GuessParameterSliceToVolume, target padding -1) against the current reconstruction.  Here all patches of the rank go through
+    the device engine in one call (rreg.register, kind SLICE_TO_VOLUME): the patch (irtkGreyImage cast, origin reset into the
+    transformation like ResetOrigin does) is the target, the reconstruction cast to short the shared source.
+    (The reference resamples a patch to the volume's voxel size into a SHADOWED variable and registers the unresampled patch,
+    patchBased2D3DRegistration.cpp:116-125: reproduced by not resampling.)"""
+
+    def __init__(self, backend, patch_attrs, patch_cube, transformations, vol_attr):
+        from . import rreg
+        self.b = backend
+        self.rreg = rreg
+        self.cube = patch_cube
+        self.T = [np.asarray(t, np.float64).reshape(4, 4).copy() for t in transformations]
+        self.vol_attr18 = rreg.attrs18(vol_attr)
+        self.attrs, self.mo = [], []
+        for a in patch_attrs:
+            a18 = rreg.attrs18(a)
+            mo = np.eye(4)
+            mo[:3, 3] = a18[6:9]
+            a18[6:9] = 0.0
+            self.attrs.append(a18); self.mo.append(mo)
+        self.i2w = np.stack([a.image_to_world().astype(np.float32).ravel() for a in patch_attrs]) if patch_attrs else np.zeros((0, 16), np.float32)
+        self.w2i = np.stack([a.world_to_image().astype(np.float32).ravel() for a in patch_attrs]) if patch_attrs else np.zeros((0, 16), np.float32)
+        self.evaluations = 0
+
+    def __call__(self, it=0):
+        from .geometry import rigid_matrix, rigid_parameters
+        n = len(self.attrs)
+        if n == 0:
+            return
+        vol = self.b.recon_copyToHost()
+        images = [self.rreg.to_grey(vol)] + [self.rreg.to_grey(self.cube[k]) for k in range(n)]
+        attrs = [self.vol_attr18] + self.attrs
+        starts = [rigid_parameters(self.T[k] @ self.mo[k]) for k in range(n)]
+        dofs, _, ev = self.rreg.register(self.b, images, attrs, list(range(1, n + 1)), [0] * n, self.rreg.SLICE_TO_VOLUME, starts)
+        self.evaluations += ev
+        for k in range(n):
+            self.T[k] = rigid_matrix(*dofs[k]) @ np.linalg.inv(self.mo[k])
+        T = np.stack([t.astype(np.float32).ravel() for t in self.T])
+        Ti = np.stack([np.linalg.inv(t).astype(np.float32).ravel() for t in self.T])
+        self.b.patches_set_matrices(self.i2w, self.w2i, T, Ti)
+
+
 def generate_2d_patches(stack: np.ndarray, attr: ImageAttributes, mask: np.ndarray, mask_attr: ImageAttributes,
                         pbb=(64, 64), stride=(32, 32), thickness=2.5):
     """PatchBasedObject::generate2DPatches (include/patchBasedObject.cuh:176-342): enumerate pbb-sized boxes on a

@@ -114,3 +114,39 @@ def test_batched_items_equal_one_at_a_time():
     for k in range(5):
         one, _, _ = rreg.register(b, [images[0], images[k + 1]], [at[0], at[k + 1]], [1], [0], 1, [starts[k]])
         np.testing.assert_array_equal(got[k], one[0])
+
+
+def test_pvr_patch_registration_equals_the_reference_per_patch():
+    """pvr.PatchRegistration (all patches of a case in one device call) against the reference's own registration object run patch
+    by patch as patchBased2D3DRegistration<T>::runHybrid does (ParallelPatchToVolumeRegistration, patchBased2D3DRegistration.cpp:88-168):
+    target = the patch cast to irtkGreyImage with its origin moved into the transformation, source = the reconstruction cast to
+    irtkGreyImage, GuessParameterSliceToVolume, target padding -1."""
+    from fetalreconstruction_b200 import rreg
+    from fetalreconstruction_b200.geometry import rigid_matrix, rigid_parameters
+    from fetalreconstruction_b200.pvr import PatchReconstruction, PatchRegistration
+    from pvr_case import make_pvr_case, setup_backend
+    case = make_pvr_case(seed=21, vol=40, n_stacks=2, slices=5, size=40, pbb=(16, 16), stride=(8, 8))
+    ds = case["ds"]
+    n = min(len(case["attrs"]), 24)
+    sub = dict(case)
+    sub["per_stack"] = [min(case["per_stack"][0], n), n - min(case["per_stack"][0], n)]
+    sub["attrs"] = case["attrs"][:n]
+    for k in ("cube", "i2w", "w2i", "T", "Tinv"):
+        sub[k] = np.ascontiguousarray(case[k][:n])
+    rng = np.random.default_rng(3)
+    start = [case["trans"][k] @ rigid_matrix(*(rng.uniform(-1, 1, 3)), *(rng.uniform(-2, 2, 3))) for k in range(n)]
+    b = setup_backend(PatchReconstruction(0), sub, device_patch_init=False)
+    # a smooth "reconstruction" to register against: the phantom itself, -1 outside the mask (what MaskVolume leaves)
+    vol = np.where(ds.mask > 0, ds.truth, -1.0).astype(np.float32)
+    b.recon_copyFromHost(vol.ravel())
+    reg = PatchRegistration(b, sub["attrs"], sub["cube"], start, ds.vol_attr)
+    reg()
+    src = ri.Image.new(rreg.attrs18(ds.vol_attr), vol.astype(np.float64))
+    moved = 0.0
+    for k in range(n):
+        a18 = rreg.attrs18(sub["attrs"][k])
+        mo = np.eye(4); mo[:3, 3] = a18[6:9]; a18[6:9] = 0
+        want = ri.rigid_register(ri.Image.new(a18, sub["cube"][k][None].astype(np.float64)), src, 1, rigid_parameters(start[k] @ mo))
+        np.testing.assert_array_equal(rigid_parameters(reg.T[k] @ mo), rigid_parameters(rigid_matrix(*want)), err_msg=f"patch {k}")
+        moved = max(moved, float(np.abs(want - rigid_parameters(start[k] @ mo)).max()))
+    assert moved > 0.05 and reg.evaluations > 100 * n
